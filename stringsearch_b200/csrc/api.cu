@@ -1,0 +1,528 @@
+// api.cu -- the extern "C" boundary declared in include/gsa.h.
+//
+// Host-side logic only: argument checks that mirror the reference's entry points,
+// device selection, host<->device staging, handle lifetime, and the sacapart fan-out.
+// All compute is in sa_build.cu / search.cu / verify.cu.  There is no CPU fallback: with
+// no usable GPU every compute entry point returns GSA_ECUDA.
+#include <algorithm>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "builder.h"
+
+namespace gsa {
+
+static thread_local std::string g_last_error;
+
+void set_error(const char *what, const char *file, int line) {
+  char buf[512];
+  snprintf(buf, sizeof buf, "%s (%s:%d)", what ? what : "unknown error", file, line);
+  g_last_error = buf;
+}
+
+namespace {
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = false;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; cudaGetLastError(); }
+    cudaError_t e = cudaSetDevice(dev);
+    ok = (e == cudaSuccess);
+    if (!ok) { set_error(cudaGetErrorString(e), __FILE__, __LINE__); cudaGetLastError(); }
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+struct Stream {
+  cudaStream_t s = nullptr;
+  int create() {
+    GSA_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    return GSA_OK;
+  }
+  ~Stream() { if (s) cudaStreamDestroy(s); }
+};
+
+template <typename T>
+struct DevBuf {
+  T *p = nullptr;
+  int alloc(size_t count) {
+    cudaError_t e = cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T) + 64);
+    if (e != cudaSuccess) {
+      p = nullptr;
+      set_error(cudaGetErrorString(e), __FILE__, __LINE__);
+      cudaGetLastError();
+      return GSA_ENOMEM;
+    }
+    return GSA_OK;
+  }
+  T *release() { T *r = p; p = nullptr; return r; }
+  ~DevBuf() { if (p) cudaFree(p); }
+};
+
+int current_device() {
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return d;
+}
+
+}  // namespace
+}  // namespace gsa
+
+using namespace gsa;
+
+struct gsa_index {
+  int device = 0;
+  u64 n = 0;           // suffix-array length == logical text length
+  u64 text_avail = 0;  // bytes resident behind d_text (n + halo)
+  u8 *d_text = nullptr;
+  i32 *d_sa = nullptr;
+  // shard bookkeeping (halo top-up needs the caller's text; see gsa_part_create)
+  const u8 *host_full = nullptr;
+  u64 n_full = 0;
+  u64 offset = 0;
+};
+
+struct gsa_part {
+  const u8 *text = nullptr;
+  u64 n = 0;
+  u64 partition_size = 0;
+  std::vector<gsa_index *> shards;
+  std::vector<int> devices;
+};
+
+extern "C" {
+
+const char *gsa_last_error(void) { return g_last_error.c_str(); }
+const char *gsa_version(void) { return "gsa 0.1 (sm_100a, prefix doubling + onesweep LSD radix)"; }
+
+int32_t gsa_device_count(void) {
+  int c = 0;
+  if (cudaGetDeviceCount(&c) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return c;
+}
+
+void *gsa_host_alloc(size_t bytes) {
+  void *p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return p;
+}
+void gsa_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+size_t gsa_build_workspace_bytes(int32_t n) { return n <= 0 ? 0 : build_workspace_bytes((u32)n); }
+
+int32_t gsa_build_device(const uint8_t *d_T, int32_t *d_SA, int32_t n, void *workspace, size_t workspace_bytes,
+                         void *stream, gsa_build_stats *stats) {
+  if (d_T == nullptr || d_SA == nullptr || n < 0) return GSA_EINVAL;
+  return build_sa_device(d_T, d_SA, (u32)n, workspace, workspace_bytes, static_cast<cudaStream_t>(stream), stats);
+}
+
+// divsufsort(T, SA, n): argument checks and the n <= 2 shortcuts are the reference's own
+// (c-sources/divsufsort.c:346-349; crates/divsufsort/src/divsufsort.rs:18-29).
+int32_t gsa_divsufsort_ex(const uint8_t *T, int32_t *SA, int32_t n, int32_t device, gsa_build_stats *stats) {
+  if (stats) memset(stats, 0, sizeof(*stats));
+  if (T == nullptr || SA == nullptr || n < 0) return GSA_EINVAL;
+  if (n == 0) return GSA_OK;
+  if (n == 1) { SA[0] = 0; return GSA_OK; }
+  if (n == 2) {
+    const int m = T[0] < T[1];
+    SA[m ^ 1] = 0;
+    SA[m] = 1;
+    return GSA_OK;
+  }
+  DeviceGuard dg(device);
+  if (!dg.ok) return GSA_ECUDA;
+  Stream st;
+  GSA_TRY_RC(st.create());
+  DevBuf<u8> d_T;
+  DevBuf<i32> d_SA;
+  GSA_TRY_RC(d_T.alloc((size_t)n + 64));
+  GSA_TRY_RC(d_SA.alloc((size_t)n));
+  cudaEvent_t e0, e1, e2, e3;
+  GSA_TRY(cudaEventCreate(&e0)); GSA_TRY(cudaEventCreate(&e1));
+  GSA_TRY(cudaEventCreate(&e2)); GSA_TRY(cudaEventCreate(&e3));
+  struct EvFree { cudaEvent_t a, b, c, d; ~EvFree() { cudaEventDestroy(a); cudaEventDestroy(b); cudaEventDestroy(c); cudaEventDestroy(d); } } evg{e0, e1, e2, e3};
+  GSA_TRY(cudaEventRecord(e0, st.s));
+  GSA_TRY(cudaMemcpyAsync(d_T.p, T, (size_t)n, cudaMemcpyHostToDevice, st.s));
+  GSA_TRY(cudaEventRecord(e1, st.s));
+  gsa_build_stats local;
+  gsa_build_stats *sp = stats ? stats : &local;
+  GSA_TRY_RC(build_sa_device(d_T.p, d_SA.p, (u32)n, nullptr, 0, st.s, sp));
+  GSA_TRY(cudaEventRecord(e2, st.s));
+  GSA_TRY(cudaMemcpyAsync(SA, d_SA.p, (size_t)n * sizeof(i32), cudaMemcpyDeviceToHost, st.s));
+  GSA_TRY(cudaEventRecord(e3, st.s));
+  GSA_TRY(cudaStreamSynchronize(st.s));
+  cudaEventElapsedTime(&sp->ms_h2d, e0, e1);
+  cudaEventElapsedTime(&sp->ms_d2h, e2, e3);
+  return GSA_OK;
+}
+
+int32_t gsa_divsufsort(const uint8_t *T, int32_t *SA, int32_t n) {
+  return gsa_divsufsort_ex(T, SA, n, current_device(), nullptr);
+}
+
+int32_t gsa_sufcheck_device(const uint8_t *d_T, const int32_t *d_SA, int32_t n, void *stream, int64_t *bad_index) {
+  if (n < 0 || (n > 0 && (d_T == nullptr || d_SA == nullptr))) return GSA_EINVAL;
+  return sufcheck_device(d_T, d_SA, (u32)n, static_cast<cudaStream_t>(stream), bad_index);
+}
+
+int32_t gsa_sufcheck(const uint8_t *T, const int32_t *SA, int32_t n, int32_t device, int64_t *bad_index) {
+  if (bad_index) *bad_index = -1;
+  if (n < 0 || (n > 0 && (T == nullptr || SA == nullptr))) return GSA_EINVAL;
+  if (n == 0) return 0;
+  DeviceGuard dg(device);
+  if (!dg.ok) return GSA_ECUDA;
+  Stream st;
+  GSA_TRY_RC(st.create());
+  DevBuf<u8> d_T;
+  DevBuf<i32> d_SA;
+  GSA_TRY_RC(d_T.alloc((size_t)n));
+  GSA_TRY_RC(d_SA.alloc((size_t)n));
+  GSA_TRY(cudaMemcpyAsync(d_T.p, T, (size_t)n, cudaMemcpyHostToDevice, st.s));
+  GSA_TRY(cudaMemcpyAsync(d_SA.p, SA, (size_t)n * 4, cudaMemcpyHostToDevice, st.s));
+  return sufcheck_device(d_T.p, d_SA.p, (u32)n, st.s, bad_index);
+}
+
+// ------------------------------------------------------------------------------------------
+// Resident index
+// ------------------------------------------------------------------------------------------
+static int index_create_impl(const u8 *T_full, u64 n_full, u64 offset, u64 len, u64 halo, int device, bool is_shard,
+                             const i32 *host_sa, gsa_index **out, gsa_build_stats *stats) {
+  if (out == nullptr) return GSA_EINVAL;
+  *out = nullptr;
+  if (stats) memset(stats, 0, sizeof(*stats));
+  if ((T_full == nullptr && n_full > 0) || offset > n_full || len > n_full - offset) return GSA_EINVAL;
+  if (len >= 0x7fffffffull) {  // crates/divsufsort/src/divsufsort.rs:9-13: text.len() < i32::MAX
+    set_error("text too large, should not exceed 2147483646 bytes", __FILE__, __LINE__);
+    return GSA_EINVAL;
+  }
+  DeviceGuard dg(device);
+  if (!dg.ok) return GSA_ECUDA;
+  halo = std::min<u64>(halo, n_full - offset - len);
+  gsa_index *ix = new (std::nothrow) gsa_index();
+  if (!ix) return GSA_ENOMEM;
+  ix->device = device;
+  ix->n = len;
+  ix->text_avail = len + halo;
+  if (is_shard) { ix->host_full = T_full; ix->n_full = n_full; ix->offset = offset; }
+  DevBuf<u8> d_T;
+  DevBuf<i32> d_SA;
+  int rc = d_T.alloc((size_t)(len + halo) + 64);
+  if (rc == GSA_OK) rc = d_SA.alloc((size_t)len);
+  Stream st;
+  if (rc == GSA_OK) rc = st.create();
+  auto body = [&]() -> int {
+    if (len + halo > 0) GSA_TRY(cudaMemcpyAsync(d_T.p, T_full + offset, (size_t)(len + halo), cudaMemcpyHostToDevice, st.s));
+    if (host_sa) {
+      if (len > 0) GSA_TRY(cudaMemcpyAsync(d_SA.p, host_sa, (size_t)len * 4, cudaMemcpyHostToDevice, st.s));
+      GSA_TRY(cudaStreamSynchronize(st.s));
+      return GSA_OK;
+    }
+    return build_sa_device(d_T.p, d_SA.p, (u32)len, nullptr, 0, st.s, stats);
+  };
+  if (rc == GSA_OK) rc = body();
+  if (rc != GSA_OK) { delete ix; return rc; }
+  ix->d_text = d_T.release();
+  ix->d_sa = d_SA.release();
+  *out = ix;
+  return GSA_OK;
+}
+
+int32_t gsa_index_create(const uint8_t *T, int64_t n, int32_t device, gsa_index **out, gsa_build_stats *stats) {
+  if (n < 0) return GSA_EINVAL;
+  return index_create_impl(T, (u64)n, 0, (u64)n, 0, device, false, nullptr, out, stats);
+}
+
+int32_t gsa_index_from_parts(const uint8_t *T, const int32_t *SA, int64_t n, int32_t device, gsa_index **out) {
+  if (n < 0 || (n > 0 && SA == nullptr)) return GSA_EINVAL;
+  static const i32 dummy = 0;
+  return index_create_impl(T, (u64)n, 0, (u64)n, 0, device, false, n > 0 ? SA : &dummy, out, nullptr);
+}
+
+int32_t gsa_index_create_shard(const uint8_t *T_full, uint64_t n_full, uint64_t offset, uint64_t len, uint64_t halo,
+                               int32_t device, gsa_index **out, gsa_build_stats *stats) {
+  return index_create_impl(T_full, n_full, offset, len, halo, device, true, nullptr, out, stats);
+}
+
+int64_t gsa_index_len(const gsa_index *ix) { return ix ? (int64_t)ix->n : -1; }
+int32_t gsa_index_device(const gsa_index *ix) { return ix ? ix->device : -1; }
+const uint8_t *gsa_index_device_text(const gsa_index *ix) { return ix ? ix->d_text : nullptr; }
+const int32_t *gsa_index_device_sa(const gsa_index *ix) { return ix ? ix->d_sa : nullptr; }
+
+int32_t gsa_index_sa(const gsa_index *ix, int32_t *out_sa) {
+  if (!ix || (ix->n > 0 && !out_sa)) return GSA_EINVAL;
+  if (ix->n == 0) return GSA_OK;
+  DeviceGuard dg(ix->device);
+  if (!dg.ok) return GSA_ECUDA;
+  GSA_TRY(cudaMemcpy(out_sa, ix->d_sa, (size_t)ix->n * 4, cudaMemcpyDeviceToHost));
+  return GSA_OK;
+}
+
+int32_t gsa_index_verify(const gsa_index *ix, int64_t *bad_index) {
+  if (!ix) return GSA_EINVAL;
+  if (ix->n == 0) return GSA_EPANIC;  // sacabase lib.rs:143: `input.len() - 1` underflows
+  DeviceGuard dg(ix->device);
+  if (!dg.ok) return GSA_ECUDA;
+  Stream st;
+  GSA_TRY_RC(st.create());
+  return sufcheck_device(ix->d_text, ix->d_sa, (u32)ix->n, st.s, bad_index);
+}
+
+void gsa_index_destroy(gsa_index *ix) {
+  if (!ix) return;
+  DeviceGuard dg(ix->device);
+  if (ix->d_text) cudaFree(ix->d_text);
+  if (ix->d_sa) cudaFree(ix->d_sa);
+  delete ix;
+}
+
+// Grow the halo behind a shard so that the may_extend rule can read `want` bytes past its end.
+static int ensure_halo(gsa_index *ix, u64 want) {
+  if (!ix->host_full) return GSA_OK;
+  const u64 room = ix->n_full - ix->offset - ix->n;
+  want = std::min(want, room);
+  if (ix->text_avail - ix->n >= want) return GSA_OK;
+  DevBuf<u8> nt;
+  GSA_TRY_RC(nt.alloc((size_t)(ix->n + want) + 64));
+  GSA_TRY(cudaMemcpy(nt.p, ix->d_text, (size_t)ix->n, cudaMemcpyDeviceToDevice));
+  GSA_TRY(cudaMemcpy(nt.p + ix->n, ix->host_full + ix->offset + ix->n, (size_t)want, cudaMemcpyHostToDevice));
+  cudaFree(ix->d_text);
+  ix->d_text = nt.release();
+  ix->text_avail = ix->n + want;
+  return GSA_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Batched search, host pointers
+// ------------------------------------------------------------------------------------------
+static TextView view_of(const gsa_index *ix) { return TextView{ix->d_text, ix->d_sa, ix->n, ix->text_avail}; }
+
+struct PatternsOnDevice {
+  DevBuf<u8> pats;
+  DevBuf<u64> off;
+  int upload(const u8 *h_pats, const u64 *h_off, u64 Q, cudaStream_t st) {
+    const u64 bytes = h_off[Q];
+    GSA_TRY_RC(pats.alloc((size_t)bytes + 64));
+    GSA_TRY_RC(off.alloc((size_t)Q + 1));
+    if (bytes) GSA_TRY(cudaMemcpyAsync(pats.p, h_pats, (size_t)bytes, cudaMemcpyHostToDevice, st));
+    GSA_TRY(cudaMemcpyAsync(off.p, h_off, (size_t)(Q + 1) * sizeof(u64), cudaMemcpyHostToDevice, st));
+    return GSA_OK;
+  }
+};
+
+static int check_patterns(const u8 *pats, const u64 *pat_off, u64 Q) {
+  if (Q == 0) return GSA_OK;
+  if (!pat_off) return GSA_EINVAL;
+  if (pat_off[Q] > 0 && !pats) return GSA_EINVAL;
+  return GSA_OK;
+}
+
+int32_t gsa_lsm_batch(const gsa_index *ix, const uint8_t *pats, const uint64_t *pat_off, uint64_t Q,
+                      uint64_t *out_start, uint32_t *out_len) {
+  if (!ix || (Q > 0 && (!out_start || !out_len))) return GSA_EINVAL;
+  GSA_TRY_RC(check_patterns(pats, pat_off, Q));
+  if (ix->n == 0) return GSA_EPANIC;
+  if (Q == 0) return GSA_OK;
+  DeviceGuard dg(ix->device);
+  if (!dg.ok) return GSA_ECUDA;
+  Stream st;
+  GSA_TRY_RC(st.create());
+  PatternsOnDevice pd;
+  GSA_TRY_RC(pd.upload(pats, pat_off, Q, st.s));
+  DevBuf<u64> d_start;
+  DevBuf<u32> d_len;
+  GSA_TRY_RC(d_start.alloc((size_t)Q));
+  GSA_TRY_RC(d_len.alloc((size_t)Q));
+  GSA_TRY_RC(lsm_device(view_of(ix), pd.pats.p, pd.off.p, Q, 0, 0, d_start.p, d_len.p, st.s));
+  GSA_TRY(cudaMemcpyAsync(out_start, d_start.p, (size_t)Q * 8, cudaMemcpyDeviceToHost, st.s));
+  GSA_TRY(cudaMemcpyAsync(out_len, d_len.p, (size_t)Q * 4, cudaMemcpyDeviceToHost, st.s));
+  GSA_TRY(cudaStreamSynchronize(st.s));
+  return GSA_OK;
+}
+
+int32_t gsa_search_all_batch(const gsa_index *ix, const uint8_t *pats, const uint64_t *pat_off, uint64_t Q,
+                             int32_t *out_left, int32_t *out_count) {
+  if (!ix || (Q > 0 && (!out_left || !out_count))) return GSA_EINVAL;
+  GSA_TRY_RC(check_patterns(pats, pat_off, Q));
+  if (Q == 0) return GSA_OK;
+  if (ix->n == 0) {  // utils.c:269,272: idx = -1, count 0 on an empty text / SA
+    for (u64 q = 0; q < Q; ++q) { out_left[q] = -1; out_count[q] = 0; }
+    return GSA_OK;
+  }
+  DeviceGuard dg(ix->device);
+  if (!dg.ok) return GSA_ECUDA;
+  Stream st;
+  GSA_TRY_RC(st.create());
+  PatternsOnDevice pd;
+  GSA_TRY_RC(pd.upload(pats, pat_off, Q, st.s));
+  DevBuf<i32> d_left, d_count;
+  GSA_TRY_RC(d_left.alloc((size_t)Q));
+  GSA_TRY_RC(d_count.alloc((size_t)Q));
+  GSA_TRY_RC(search_all_device(view_of(ix), pd.pats.p, pd.off.p, Q, d_left.p, d_count.p, st.s));
+  GSA_TRY(cudaMemcpyAsync(out_left, d_left.p, (size_t)Q * 4, cudaMemcpyDeviceToHost, st.s));
+  GSA_TRY(cudaMemcpyAsync(out_count, d_count.p, (size_t)Q * 4, cudaMemcpyDeviceToHost, st.s));
+  GSA_TRY(cudaStreamSynchronize(st.s));
+  return GSA_OK;
+}
+
+int32_t gsa_contains_batch(const gsa_index *ix, const uint8_t *pats, const uint64_t *pat_off, uint64_t Q,
+                           uint8_t *out) {
+  if (Q > 0 && !out) return GSA_EINVAL;
+  std::vector<i32> left((size_t)Q), count((size_t)Q);
+  GSA_TRY_RC(gsa_search_all_batch(ix, pats, pat_off, Q, left.data(), count.data()));
+  for (u64 q = 0; q < Q; ++q) out[q] = count[q] > 0;
+  return GSA_OK;
+}
+
+int32_t gsa_lsm_device(const gsa_index *ix, const uint8_t *d_pats, const uint64_t *d_pat_off, uint64_t Q,
+                       uint64_t offset, int32_t accumulate, uint64_t *d_io_start, uint32_t *d_io_len, void *stream) {
+  if (!ix || (Q > 0 && (!d_pat_off || !d_io_start || !d_io_len))) return GSA_EINVAL;
+  return lsm_device(view_of(ix), d_pats, d_pat_off, Q, offset, accumulate, d_io_start, d_io_len,
+                    static_cast<cudaStream_t>(stream));
+}
+
+int32_t gsa_search_all_device(const gsa_index *ix, const uint8_t *d_pats, const uint64_t *d_pat_off, uint64_t Q,
+                              int32_t *d_out_left, int32_t *d_out_count, void *stream) {
+  if (!ix || (Q > 0 && (!d_pat_off || !d_out_left || !d_out_count))) return GSA_EINVAL;
+  if (ix->n == 0) return GSA_EINVAL;
+  return search_all_device(view_of(ix), d_pats, d_pat_off, Q, d_out_left, d_out_count,
+                           static_cast<cudaStream_t>(stream));
+}
+
+int32_t gsa_lsm_reduce_device(uint64_t *d_start, uint32_t *d_len, uint64_t Q, uint32_t nsets, void *stream) {
+  if (Q > 0 && (!d_start || !d_len)) return GSA_EINVAL;
+  return lsm_reduce_device(d_start, d_len, Q, nsets, static_cast<cudaStream_t>(stream));
+}
+
+// ------------------------------------------------------------------------------------------
+// Partitioned suffix array (sacapart)
+// ------------------------------------------------------------------------------------------
+static const u64 kDefaultHalo = 4096;
+
+int32_t gsa_part_create(const uint8_t *T, uint64_t n, uint64_t num_partitions, const int32_t *devices, int32_t ndev,
+                        gsa_part **out) {
+  if (!out) return GSA_EINVAL;
+  *out = nullptr;
+  if (T == nullptr && n > 0) return GSA_EINVAL;
+  if (num_partitions == 0) {  // sacapart lib.rs:43 divides by zero
+    set_error("attempt to divide by zero (num_partitions == 0)", __FILE__, __LINE__);
+    return GSA_EPANIC;
+  }
+  gsa_part *p = new (std::nothrow) gsa_part();
+  if (!p) return GSA_ENOMEM;
+  p->text = T;
+  p->n = n;
+  p->partition_size = n / num_partitions + 1;                        // lib.rs:43
+  const u64 nparts = (n + p->partition_size - 1) / p->partition_size;  // par_chunks, lib.rs:45-49
+  if (devices && ndev > 0) p->devices.assign(devices, devices + ndev);
+  else p->devices.push_back(current_device());
+  p->shards.assign((size_t)nparts, nullptr);
+  const size_t nd = p->devices.size();
+  std::vector<int> rcs(nd, GSA_OK);
+  std::vector<std::string> errs(nd);
+  // One host thread per device (rayon's par_chunks in the reference); shards that share a
+  // device are built one after the other so each can use the whole GPU and its workspace.
+  auto worker = [&](size_t k) {
+    for (u64 i = k; i < nparts; i += nd) {
+      const u64 off = i * p->partition_size;
+      const u64 len = std::min(p->partition_size, n - off);
+      int rc = gsa_index_create_shard(T, n, off, len, kDefaultHalo, p->devices[k], &p->shards[(size_t)i], nullptr);
+      if (rc != GSA_OK) { rcs[k] = rc; errs[k] = g_last_error; return; }
+    }
+  };
+  if (nd == 1) {
+    worker(0);
+  } else {
+    std::vector<std::thread> th;
+    for (size_t k = 0; k < nd; ++k) th.emplace_back(worker, k);
+    for (auto &t : th) t.join();
+  }
+  for (size_t k = 0; k < nd; ++k)
+    if (rcs[k] != GSA_OK) {
+      g_last_error = errs[k];
+      const int rc = rcs[k];
+      gsa_part_destroy(p);
+      return rc;
+    }
+  *out = p;
+  return GSA_OK;
+}
+
+uint64_t gsa_part_num_partitions(const gsa_part *p) { return p ? p->shards.size() : 0; }
+uint64_t gsa_part_partition_size(const gsa_part *p) { return p ? p->partition_size : 0; }
+const gsa_index *gsa_part_shard(const gsa_part *p, uint64_t i) {
+  return (p && i < p->shards.size()) ? p->shards[(size_t)i] : nullptr;
+}
+
+void gsa_part_destroy(gsa_part *p) {
+  if (!p) return;
+  for (gsa_index *ix : p->shards) gsa_index_destroy(ix);
+  delete p;
+}
+
+int32_t gsa_part_lsm_batch(gsa_part *p, const uint8_t *pats, const uint64_t *pat_off, uint64_t Q, uint64_t *out_start,
+                           uint32_t *out_len) {
+  if (!p || (Q > 0 && (!out_start || !out_len))) return GSA_EINVAL;
+  GSA_TRY_RC(check_patterns(pats, pat_off, Q));
+  if (p->shards.empty()) {  // lib.rs:94-96: expect() on None
+    set_error("partitioned suffix arrays should always find at least one longest common substring", __FILE__, __LINE__);
+    return GSA_EPANIC;
+  }
+  if (Q == 0) return GSA_OK;
+  u64 max_len = 0;
+  for (u64 q = 0; q < Q; ++q) max_len = std::max(max_len, pat_off[q + 1] - pat_off[q]);
+
+  const size_t nd = p->devices.size();
+  struct PerDev {
+    Stream st;
+    PatternsOnDevice pd;
+    DevBuf<u64> start;
+    DevBuf<u32> len;
+    bool used = false;
+  };
+  std::vector<PerDev> dev(nd);
+  // fan out: every device answers for its shards, in ascending shard order (strict-greater
+  // replacement then keeps the earliest partition, lib.rs:86-92)
+  for (size_t k = 0; k < nd; ++k) {
+    if (k >= p->shards.size()) break;
+    DeviceGuard dg(p->devices[k]);
+    if (!dg.ok) return GSA_ECUDA;
+    PerDev &d = dev[k];
+    d.used = true;
+    GSA_TRY_RC(d.st.create());
+    GSA_TRY_RC(d.pd.upload(pats, pat_off, Q, d.st.s));
+    // device 0 receives every device's result set for the final merge
+    GSA_TRY_RC(d.start.alloc((size_t)Q * (k == 0 ? nd : 1)));
+    GSA_TRY_RC(d.len.alloc((size_t)Q * (k == 0 ? nd : 1)));
+    bool first = true;
+    for (size_t i = k; i < p->shards.size(); i += nd) {
+      gsa_index *ix = p->shards[i];
+      GSA_TRY_RC(ensure_halo(ix, max_len));
+      GSA_TRY_RC(lsm_device(view_of(ix), d.pd.pats.p, d.pd.off.p, Q, ix->offset, first ? 0 : 1, d.start.p, d.len.p,
+                            d.st.s));
+      first = false;
+    }
+  }
+  u32 nsets = 0;
+  for (size_t k = 0; k < nd; ++k) {
+    if (!dev[k].used) continue;
+    DeviceGuard dg(p->devices[k]);
+    GSA_TRY(cudaStreamSynchronize(dev[k].st.s));
+    ++nsets;
+  }
+  // gather to device 0 and merge there
+  DeviceGuard dg0(p->devices[0]);
+  for (size_t k = 1; k < nd; ++k) {
+    if (!dev[k].used) continue;
+    GSA_TRY(cudaMemcpyPeerAsync(dev[0].start.p + (size_t)k * Q, p->devices[0], dev[k].start.p, p->devices[k], (size_t)Q * 8, dev[0].st.s));
+    GSA_TRY(cudaMemcpyPeerAsync(dev[0].len.p + (size_t)k * Q, p->devices[0], dev[k].len.p, p->devices[k], (size_t)Q * 4, dev[0].st.s));
+  }
+  GSA_TRY_RC(lsm_reduce_device(dev[0].start.p, dev[0].len.p, Q, nsets, dev[0].st.s));
+  GSA_TRY(cudaMemcpyAsync(out_start, dev[0].start.p, (size_t)Q * 8, cudaMemcpyDeviceToHost, dev[0].st.s));
+  GSA_TRY(cudaMemcpyAsync(out_len, dev[0].len.p, (size_t)Q * 4, cudaMemcpyDeviceToHost, dev[0].st.s));
+  GSA_TRY(cudaStreamSynchronize(dev[0].st.s));
+  return GSA_OK;
+}
+
+}  // extern "C"

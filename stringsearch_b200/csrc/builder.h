@@ -1,0 +1,38 @@
+// builder.h -- internal (non-ABI) interfaces between the .cu translation units.
+#pragma once
+#include <string.h>
+
+#include "common.cuh"
+
+namespace gsa {
+
+struct RoundResult {
+  u32 live_out;    // suffixes still in non-singleton groups after the round
+  u32 groups_out;  // number of such groups
+};
+
+// sa_build.cu
+size_t build_workspace_bytes(u32 n);
+int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t workspace_bytes, cudaStream_t st,
+                    gsa_build_stats *stats);
+
+// verify.cu
+size_t sufcheck_workspace_bytes(u32 n);
+int sufcheck_device(const u8 *d_T, const i32 *d_SA, u32 n, cudaStream_t st, i64 *bad_index);
+
+// search.cu
+// Text view of an index: the suffix array covers text[0, n); text_avail >= n bytes are
+// readable (halo behind a shard, used only by the may_extend rule).
+struct TextView {
+  const u8 *text;
+  const i32 *sa;
+  u64 n;
+  u64 text_avail;
+};
+int lsm_device(const TextView &tv, const u8 *d_pats, const u64 *d_pat_off, u64 Q, u64 offset, int accumulate,
+               u64 *d_io_start, u32 *d_io_len, cudaStream_t st);
+int search_all_device(const TextView &tv, const u8 *d_pats, const u64 *d_pat_off, u64 Q, i32 *d_left, i32 *d_count,
+                      cudaStream_t st);
+int lsm_reduce_device(u64 *d_start, u32 *d_len, u64 Q, u32 nsets, cudaStream_t st);
+
+}  // namespace gsa

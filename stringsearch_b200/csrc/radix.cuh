@@ -1,0 +1,254 @@
+// radix.cuh -- hand-written LSD radix sort building blocks for (u64 key, u32 value)
+// pairs on sm_100a.  No CUB / Thrust.
+//
+//   hist_add()          warp-aggregated multi-digit histogram update (match.any on the
+//                       whole key, one shared-memory atomic per digit per distinct key)
+//   k_scan_hist         per-digit exclusive scan of the global histograms + detection
+//                       of constant digits (their pass is skipped by the host)
+//   k_radix_pass        one "onesweep" pass: a tile is ranked in shared memory with
+//                       warp match.any, its per-digit counts are chained to the
+//                       preceding tiles by a decoupled look-back, and keys/values are
+//                       scattered in digit runs.  Optionally generates the round-0 keys
+//                       on the fly from the bit-packed text (GEN) so they are never
+//                       materialised unsorted.
+//
+// Traffic per pass and element: 12 B read + 12 B written (8 B key + 4 B value) -- the
+// HBM roofline this kernel is measured against ("kernels").
+#pragma once
+#include "common.cuh"
+
+namespace gsa {
+
+constexpr int RADIX_BITS = 8;
+constexpr int RADIX = 1 << RADIX_BITS;
+constexpr int MAX_PASSES = 8;
+
+// ---------------------------------------------------------------------------------
+// Round-0 key generation from the bit-packed symbol stream.
+//   packed : big-endian bit stream, `b` bits per symbol, symbol i at bits [i*b, i*b+b)
+//            counted from the MSB of word 0; zero beyond the text end (>= 2 spare words)
+//   element j of the initial sequence is suffix i(j): the `ns` short suffixes (fewer than
+//   symbols_per_key symbols left) come first, shortest first, then 0,1,2,...  A stable
+//   sort keeps a short suffix in front of every longer suffix that shares its zero-padded
+//   key, which is exactly "a proper prefix sorts first".
+// ---------------------------------------------------------------------------------
+struct KeyGen {
+  const u64 *packed;
+  u32 n;         // text length
+  u32 ns;        // number of short suffixes = min(symbols_per_key - 1, n)
+  u32 b;         // bits per symbol
+  u32 key_bits;  // symbols_per_key * b  (1..64)
+};
+
+#ifdef __CUDACC__
+__device__ __forceinline__ void gen_key0(const KeyGen &g, u32 j, u64 &key, u32 &sufx) {
+  const u32 i = (j < g.ns) ? (g.n - 1u - j) : (j - g.ns);
+  const u64 bit = (u64)i * g.b;
+  const u64 w = bit >> 6;
+  const u32 s = (u32)bit & 63u;
+  const u64 w0 = __ldg(g.packed + w);
+  const u64 w1 = __ldg(g.packed + w + 1);
+  const u64 x = s ? ((w0 << s) | (w1 >> (64u - s))) : w0;
+  key = x >> (64u - g.key_bits);
+  sufx = i;
+}
+
+// Warp-aggregated histogram update for `npass` 8-bit digits of `key` (digit p = bits
+// [8p, 8p+8)).  Lanes holding the same key elect a leader which adds the multiplicity
+// once per digit, so runs of identical keys (the common case in doubling rounds) do
+// not serialise on one shared-memory address.  Must be called by all lanes of the warp
+// (valid = false for lanes without an element).
+__device__ __forceinline__ void hist_add(u32 *shist, u64 key, bool valid, int npass) {
+  const u32 act = __ballot_sync(0xffffffffu, valid);
+  if (valid) {
+    const u32 peers = __match_any_sync(act, key);
+    if (lane_id() == (u32)(31 - __clz(peers))) {
+      const u32 c = __popc(peers);
+      for (int p = 0; p < npass; ++p) atomicAdd(&shist[p * RADIX + (u32)((key >> (8 * p)) & 255u)], c);
+    }
+  }
+}
+
+// ghist[p][256] -> bin_base[p][256] (exclusive scan); sets bit p of *skip_mask when one
+// bin of digit p holds all `total` elements (the pass would be the identity).
+__global__ void __launch_bounds__(RADIX) k_scan_hist(const u32 *__restrict__ ghist, u32 *__restrict__ bin_base,
+                                                     u32 total, u32 *__restrict__ skip_mask) {
+  __shared__ u32 wsum[RADIX / 32];
+  const int p = blockIdx.x, t = threadIdx.x, lane = t & 31, w = t >> 5;
+  const u32 c = ghist[p * RADIX + t];
+  if (c == total && total != 0) atomicOr(skip_mask, 1u << p);
+  u32 x = c;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    u32 y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
+  }
+  if (lane == 31) wsum[w] = x;
+  __syncthreads();
+  u32 add = 0;
+  for (int i = 0; i < w; ++i) add += wsum[i];
+  bin_base[p * RADIX + t] = x - c + add;
+}
+
+// Tile status word of the pass look-back: 0 = not ready, otherwise value+1 in bits 0..30
+// and bit 31 = "inclusive prefix" (else "tile aggregate").  value <= n <= 2^31-2.
+__device__ __forceinline__ u32 st_agg(u32 v) { return v + 1u; }
+__device__ __forceinline__ u32 st_pre(u32 v) { return (v + 1u) | 0x80000000u; }
+
+struct PassArgs {
+  const u64 *keys_in;
+  const u32 *vals_in;
+  u64 *keys_out;
+  u32 *vals_out;
+  u32 n;               // elements
+  u32 shift;           // digit = (key >> shift) & 255
+  const u32 *bin_base; // [256] global exclusive offsets of this digit
+  u32 *status;         // [tiles][256], zeroed before launch
+  u32 *counter;        // dynamic tile id, zeroed before launch
+  KeyGen gen;          // GEN only
+};
+
+template <int THREADS, int IPT>
+struct PassCfg {
+  static constexpr int WARPS = THREADS / 32;
+  static constexpr int TILE = THREADS * IPT;
+  static constexpr size_t SMEM = (size_t)TILE * 8 + (size_t)TILE * 4 + (size_t)WARPS * RADIX * 4 + RADIX * 4 + RADIX * 4;
+};
+
+template <int THREADS, int IPT, bool GEN>
+__global__ void __launch_bounds__(THREADS) k_radix_pass(const PassArgs a) {
+  static_assert(THREADS >= RADIX && THREADS % 32 == 0, "one thread per bin is assumed");
+  constexpr int WARPS = THREADS / 32;
+  constexpr int TILE = THREADS * IPT;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  u64 *skeys = reinterpret_cast<u64 *>(smem_raw);          // [TILE]
+  u32 *svals = reinterpret_cast<u32 *>(skeys + TILE);      // [TILE]
+  u32 *whist = svals + TILE;                               // [WARPS][256] counts -> running offsets
+  u32 *bin_excl = whist + WARPS * RADIX;                   // [256] tile-local exclusive offset of each bin
+  u32 *bin_gofs = bin_excl + RADIX;                        // [256] global offset - local offset
+  __shared__ u32 s_tile;
+  __shared__ u32 s_wsum[RADIX / 32];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_tile = atomicAdd(a.counter, 1u);
+  for (int i = tid; i < WARPS * RADIX; i += THREADS) whist[i] = 0;
+  __syncthreads();
+  const u32 tile = s_tile;
+  const u32 tile_base = tile * (u32)TILE;
+  const u32 valid = min((u32)TILE, a.n - tile_base);
+
+  // ---- load (warp-striped: element order inside the tile is (warp, k, lane)) ----------
+  u64 key[IPT];
+  u32 val[IPT];
+  const u32 wbase = tile_base + (u32)warp * (32u * IPT) + (u32)lane;
+#pragma unroll
+  for (int k = 0; k < IPT; ++k) {
+    const u32 idx = wbase + (u32)k * 32u;
+    if (idx < a.n) {
+      if (GEN) {
+        gen_key0(a.gen, idx, key[k], val[k]);
+      } else {
+        key[k] = ld_stream_u64(a.keys_in + idx);
+        val[k] = ld_stream_u32(a.vals_in + idx);
+      }
+    } else {
+      key[k] = ~0ull;  // digit 255 at every shift; sits behind every real element of the tile
+      val[k] = 0;
+    }
+  }
+
+  // ---- per-warp digit counts (match.any: one shared atomic per distinct digit) ---------
+  u32 m[IPT];
+#pragma unroll
+  for (int k = 0; k < IPT; ++k) {
+    const u32 d = (u32)(key[k] >> a.shift) & 255u;
+    m[k] = __match_any_sync(0xffffffffu, d);
+    if (lane == 31 - __clz(m[k])) atomicAdd(&whist[warp * RADIX + d], (u32)__popc(m[k]));
+  }
+  __syncthreads();
+
+  // ---- bin totals, per-warp offsets, exclusive scan over bins; publish the aggregate ----
+  u32 cnt = 0, pub = 0;
+  if (tid < RADIX) {
+#pragma unroll
+    for (int w = 0; w < WARPS; ++w) {
+      const u32 c = whist[w * RADIX + tid];
+      whist[w * RADIX + tid] = cnt;
+      cnt += c;
+    }
+    pub = cnt - ((tid == RADIX - 1) ? ((u32)TILE - valid) : 0u);  // padding is not data
+    if (tile == 0)
+      st_volatile_u32(a.status + tid, st_pre(pub));
+    else
+      st_volatile_u32(a.status + (size_t)tile * RADIX + tid, st_agg(pub));
+    u32 x = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const u32 y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) s_wsum[warp] = x;
+    cnt = x - cnt;  // exclusive within the warp
+  }
+  __syncthreads();
+  if (tid < RADIX) {
+    u32 add = 0;
+    for (int i = 0; i < warp; ++i) add += s_wsum[i];
+    const u32 ex = cnt + add;
+    bin_excl[tid] = ex;
+#pragma unroll
+    for (int w = 0; w < WARPS; ++w) whist[w * RADIX + tid] += ex;
+  }
+  __syncthreads();
+
+  // ---- rank inside the tile (stable) and stage in shared memory -------------------------
+  const u32 lt = lanemask_lt();
+#pragma unroll
+  for (int k = 0; k < IPT; ++k) {
+    const u32 d = (u32)(key[k] >> a.shift) & 255u;
+    const u32 peers = m[k];
+    const u32 base = whist[warp * RADIX + d];
+    __syncwarp();
+    if (lane == 31 - __clz(peers)) whist[warp * RADIX + d] = base + (u32)__popc(peers);
+    __syncwarp();
+    m[k] = base + (u32)__popc(peers & lt);
+  }
+#pragma unroll
+  for (int k = 0; k < IPT; ++k) {
+    skeys[m[k]] = key[k];
+    svals[m[k]] = val[k];
+  }
+
+  // ---- decoupled look-back: one thread per bin ------------------------------------------
+  if (tid < RADIX) {
+    u32 excl = 0;
+    if (tile != 0) {
+      const u32 *st = a.status + (size_t)(tile - 1) * RADIX + tid;
+      for (;;) {
+        u32 s;
+        do { s = ld_volatile_u32(st); } while (s == 0u);
+        excl += (s & 0x7fffffffu) - 1u;
+        if (s & 0x80000000u) break;
+        st -= RADIX;
+      }
+      st_volatile_u32(a.status + (size_t)tile * RADIX + tid, st_pre(excl + pub));
+    }
+    bin_gofs[tid] = a.bin_base[tid] + excl - bin_excl[tid];
+  }
+  __syncthreads();
+
+  // ---- scatter: consecutive threads write consecutive slots of a digit run -----------------
+#pragma unroll
+  for (int k = 0; k < IPT; ++k) {
+    const u32 e = (u32)k * THREADS + (u32)tid;
+    if (e < valid) {
+      const u64 kx = skeys[e];
+      const u32 o = bin_gofs[(u32)(kx >> a.shift) & 255u] + e;
+      a.keys_out[o] = kx;
+      a.vals_out[o] = svals[e];
+    }
+  }
+}
+#endif  // __CUDACC__
+
+}  // namespace gsa

@@ -1,0 +1,45 @@
+"""divsufsort::sort / sort_in_place on the GPU.
+
+Mirrors crates/divsufsort/src/lib.rs:20-29 (and its twin crates/cdivsufsort/src/lib.rs:9-30):
+same names, same argument meaning, and the reference's panics become Python exceptions
+raised at the same preconditions.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _native as N
+from .sacabase import SuffixArray
+
+I32_MAX = 2**31 - 1
+
+
+def sort_in_place(text, sa: np.ndarray, device: int | None = None, stats: N.BuildStats | None = None) -> None:
+    """Sort suffixes of `text` and store their lexicographic order in `sa` (int32).
+
+    Panics (AssertionError) like the reference when ``len(sa) != len(text)``
+    (divsufsort.rs:4-8) or ``len(text) >= i32::MAX`` (divsufsort.rs:9-13).
+    """
+    t = N.as_u8(text)
+    if not (isinstance(sa, np.ndarray) and sa.dtype == np.int32 and sa.flags.c_contiguous and sa.flags.writeable):
+        raise TypeError("sa must be a writable C-contiguous int32 ndarray")
+    assert t.size == sa.size, "text and suffix array should have same len"
+    assert t.size < I32_MAX, f"text too large, should not exceed {I32_MAX - 1} bytes"
+    if device is None and stats is None:
+        rc = N.lib.gsa_divsufsort(N.ptr(t) if t.size else N.ptr(np.zeros(1, np.uint8)),
+                                  N.ptr(sa) if sa.size else N.ptr(np.zeros(1, np.int32)), t.size)
+    else:
+        rc = N.lib.gsa_divsufsort_ex(N.ptr(t) if t.size else N.ptr(np.zeros(1, np.uint8)),
+                                     N.ptr(sa) if sa.size else N.ptr(np.zeros(1, np.int32)), t.size,
+                                     0 if device is None else device, C.byref(stats) if stats is not None else None)
+    assert rc == 0, f"divsufsort returned {rc}: {N.last_error()}"  # cdivsufsort lib.rs:22 assert_eq!(0, ret)
+
+
+def sort(text, device: int | None = None, stats: N.BuildStats | None = None) -> SuffixArray:
+    """-> sacabase.SuffixArray (text borrowed, sa owned), like divsufsort::sort (lib.rs:25-29)."""
+    t = N.as_u8(text)
+    sa = np.zeros(t.size, dtype=np.int32)
+    sort_in_place(t, sa, device=device, stats=stats)
+    return SuffixArray(t, sa)

@@ -1,0 +1,224 @@
+"""sacapart::PartitionedSuffixArray on one or more GPUs.
+
+Mirrors crates/sacapart/src/lib.rs:26-98.  Two deployments:
+
+* ``PartitionedSuffixArray``: one process driving `devices` (shard i lives on
+  devices[i % len(devices)]), everything inside libgsa.so (gsa_part_*).
+* ``DistributedPartitionedSuffixArray``: one process per GPU under torch.distributed
+  (NCCL on GPUs, gloo in the CPU tests).  Rank r owns shards i with i % world == r; shards
+  are built with no communication; a query broadcasts the pattern batch, every rank
+  answers for its shards, and the per-rank (start, len) sets are all-gathered and merged
+  with the reference's tie rule (longer wins; equal length -> lower partition).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _native as N
+from .sacabase import LongestCommonSubstring, StringIndex
+
+
+def partition_plan(n: int, num_partitions: int):
+    """(partition_size, actual number of partitions): lib.rs:43 and par_chunks :45-49,60-62."""
+    if num_partitions == 0:
+        raise ZeroDivisionError("attempt to divide by zero")  # lib.rs:43
+    ps = n // num_partitions + 1
+    return ps, (n + ps - 1) // ps
+
+
+class PartitionedSuffixArray(StringIndex):
+    def __init__(self, text, num_partitions: int, devices=None):
+        """PartitionedSuffixArray::new(text, num_partitions, divsufsort::sort) (lib.rs:39-58).
+
+        The builder closure of the reference is fixed to the GPU divsufsort; `devices`
+        (default: the current device) says where the shards go.
+        """
+        self._text = N.as_u8(text)
+        if num_partitions == 0:
+            raise ZeroDivisionError("attempt to divide by zero")
+        devs = None
+        nd = 0
+        if devices is not None:
+            devs = (C.c_int32 * len(devices))(*devices)
+            nd = len(devices)
+        h = C.c_void_p()
+        rc = N.lib.gsa_part_create(N.ptr(self._text), self._text.size, num_partitions, devs, nd, C.byref(h))
+        N.check(rc, "gsa_part_create")
+        self._h = h
+
+    def num_partitions(self) -> int:
+        """lib.rs:60-62"""
+        return int(N.lib.gsa_part_num_partitions(self._h))
+
+    def partition_size(self) -> int:
+        return int(N.lib.gsa_part_partition_size(self._h))
+
+    def shard_sa(self, i: int) -> np.ndarray:
+        ix = N.lib.gsa_part_shard(self._h, i)
+        n = N.lib.gsa_index_len(ix)
+        out = np.empty(n, dtype=np.int32)
+        N.check(N.lib.gsa_index_sa(ix, N.ptr(out)), "gsa_index_sa")
+        return out
+
+    def longest_substring_match_batch(self, needles):
+        flat, off = N.pack_patterns(needles)
+        q = off.size - 1
+        start = np.empty(q, dtype=np.uint64)
+        length = np.empty(q, dtype=np.uint32)
+        rc = N.lib.gsa_part_lsm_batch(self._h, N.ptr(flat), N.ptr(off), q, N.ptr(start), N.ptr(length))
+        if rc == N.GSA_EPANIC:
+            raise RuntimeError("partitioned suffix arrays should always find at least one longest common substring")
+        N.check(rc, "gsa_part_lsm_batch")
+        return start, length
+
+    def longest_substring_match(self, needle) -> LongestCommonSubstring:
+        """lib.rs:69-97"""
+        s, l = self.longest_substring_match_batch([needle])
+        return LongestCommonSubstring(self._text, int(s[0]), int(l[0]))
+
+    def close(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            N.lib.gsa_part_destroy(h)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def merge_results(starts: np.ndarray, lens: np.ndarray):
+    """Host statement of the cross-rank merge rule used by the distributed query
+    (sacapart lib.rs:86-92): starts/lens are [nsets, Q]; longer wins, equal length -> the
+    smaller start (= the lower partition, partitions being disjoint ascending ranges).
+    Used by the gloo tests to check the device reduction; the product path reduces on the GPU."""
+    best_s, best_l = starts[0].copy(), lens[0].copy()
+    for s, l in zip(starts[1:], lens[1:]):
+        take = (l > best_l) | ((l == best_l) & (s < best_s))
+        best_s[take], best_l[take] = s[take], l[take]
+    return best_s, best_l
+
+
+class DistributedPartitionedSuffixArray(StringIndex):
+    """One rank per GPU; see module docstring.  `text` is the full text on every rank (the
+    reference's `&'a [u8]`); each rank uploads and indexes only its own shards (+ halo)."""
+
+    def __init__(self, text, num_partitions: int, device: int, group=None, halo: int = 4096):
+        import torch.distributed as dist
+
+        self._dist = dist
+        self._group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self._text = N.as_u8(text)
+        self._device = device
+        self._ps, self._np = partition_plan(self._text.size, num_partitions)
+        self._halo = halo
+        self._shards = []  # (partition index, offset, handle)
+        for i in range(self.rank, self._np, self.world):
+            off = i * self._ps
+            ln = min(self._ps, self._text.size - off)
+            self._shards.append((i, off, self._build_shard(off, ln)))
+
+    # The two methods below are the only device-touching steps.  The gloo CPU tests override
+    # them with the oracle to exercise the collective plumbing without a GPU; the product
+    # implementation has no such path.
+    def _build_shard(self, off: int, ln: int):
+        h = C.c_void_p()
+        rc = N.lib.gsa_index_create_shard(N.ptr(self._text), self._text.size, off, ln, self._halo, self._device,
+                                          C.byref(h), None)
+        N.check(rc, "gsa_index_create_shard")
+        return h
+
+    def _answer_local(self, t_pat, t_off, q, t_start, t_len, dev) -> None:
+        import torch
+
+        if not torch.cuda.is_available():
+            raise RuntimeError("stringsearch_b200 has no CPU path: shards need a CUDA device")
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        for k, (_, offset, h) in enumerate(self._shards):
+            rc = N.lib.gsa_lsm_device(h, t_pat.data_ptr(), t_off.data_ptr(), q, offset, 0 if k == 0 else 1,
+                                      t_start.data_ptr(), t_len.data_ptr(), stream)
+            N.check(rc, "gsa_lsm_device")
+
+    def _destroy_shard(self, h) -> None:
+        N.lib.gsa_index_destroy(h)
+
+    def num_partitions(self) -> int:
+        return self._np
+
+    def local_partitions(self):
+        return [i for i, _, _ in self._shards]
+
+    def longest_substring_match_batch(self, needles, src: int = 0):
+        """Collective: every rank calls it; `needles` is only read on rank `src`.
+        Returns (start, len) numpy arrays on every rank."""
+        import torch
+
+        dist = self._dist
+        if self._np == 0:
+            raise RuntimeError("partitioned suffix arrays should always find at least one longest common substring")
+        on_gpu = torch.cuda.is_available()
+        dev = torch.device("cuda", self._device) if on_gpu else torch.device("cpu")
+        # ---- broadcast the pattern batch ------------------------------------------------
+        if self.rank == src:
+            flat, off = N.pack_patterns(needles)
+            hdr = torch.tensor([off.size - 1, flat.size], dtype=torch.int64, device=dev)
+        else:
+            hdr = torch.zeros(2, dtype=torch.int64, device=dev)
+        if self.world > 1:
+            dist.broadcast(hdr, src=src, group=self._group)
+        q, nbytes = int(hdr[0]), int(hdr[1])
+        if self.rank == src:
+            t_off = torch.from_numpy(off.astype(np.int64)).to(dev)
+            t_pat = torch.from_numpy(flat if flat.size else np.zeros(1, np.uint8)).to(dev)
+        else:
+            t_off = torch.empty(q + 1, dtype=torch.int64, device=dev)
+            t_pat = torch.empty(max(1, nbytes), dtype=torch.uint8, device=dev)
+        if self.world > 1:
+            dist.broadcast(t_off, src=src, group=self._group)
+            dist.broadcast(t_pat, src=src, group=self._group)
+        max_len = int((t_off[1:] - t_off[:-1]).max()) if q else 0
+        if max_len > self._halo + 1:
+            raise ValueError(f"needle of {max_len} bytes exceeds the shard halo ({self._halo}); rebuild with a larger halo")
+        # ---- local shards, ascending partition index --------------------------------------
+        t_start = torch.zeros(q, dtype=torch.int64, device=dev)
+        t_len = torch.zeros(q, dtype=torch.int32, device=dev)
+        if self._shards:
+            self._answer_local(t_pat, t_off, q, t_start, t_len, dev)
+        else:
+            t_start.fill_(2**62)  # a rank without shards never wins (len 0, huge start)
+        # ---- gather + merge ---------------------------------------------------------------------
+        if self.world > 1:
+            g_start = torch.empty(self.world * q, dtype=torch.int64, device=dev)
+            g_len = torch.empty(self.world * q, dtype=torch.int32, device=dev)
+            dist.all_gather_into_tensor(g_start, t_start, group=self._group)
+            dist.all_gather_into_tensor(g_len, t_len, group=self._group)
+            if on_gpu:
+                stream = torch.cuda.current_stream(dev).cuda_stream
+                rc = N.lib.gsa_lsm_reduce_device(g_start.data_ptr(), g_len.data_ptr(), q, self.world, stream)
+                N.check(rc, "gsa_lsm_reduce_device")
+                t_start, t_len = g_start[:q], g_len[:q]
+            else:  # gloo CPU tests of the plumbing only (no shards can exist without a GPU)
+                s, l = merge_results(g_start.view(self.world, q).numpy().astype(np.uint64),
+                                     g_len.view(self.world, q).numpy().astype(np.uint32))
+                return s, l
+        return t_start.cpu().numpy().astype(np.uint64), t_len.cpu().numpy().astype(np.uint32)
+
+    def longest_substring_match(self, needle) -> LongestCommonSubstring:
+        s, l = self.longest_substring_match_batch([needle])
+        return LongestCommonSubstring(self._text, int(s[0]), int(l[0]))
+
+    def close(self):
+        for _, _, h in self._shards:
+            self._destroy_shard(h)
+        self._shards = []
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

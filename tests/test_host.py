@@ -1,0 +1,107 @@
+"""Host-side logic and the C-ABI surface, no GPU needed."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, random_cases
+
+
+def test_library_exports_every_declared_symbol():
+    from stringsearch_b200 import _native as N
+
+    hdr = open(os.path.join(ROOT, "include", "gsa.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(gsa_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 30
+    lib = C.CDLL(N.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/gsa.h but not exported by libgsa.so"
+    assert declared == set(N.EXPORTED_SYMBOLS), declared ^ set(N.EXPORTED_SYMBOLS)
+
+
+def test_library_is_sm100a_only():
+    import subprocess
+    from stringsearch_b200 import _native as N
+
+    out = subprocess.run(["cuobjdump", "-lelf", N.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_argument_checks_without_gpu():
+    """The reference's own precondition / tiny-input behaviour (divsufsort.c:346-349) is host logic."""
+    from stringsearch_b200 import _native as N
+
+    L = N.lib
+    t = np.frombuffer(b"ba", np.uint8)
+    sa = np.zeros(2, np.int32)
+    assert L.gsa_divsufsort(None, N.ptr(sa), 2) == N.GSA_EINVAL
+    assert L.gsa_divsufsort(N.ptr(t), None, 2) == N.GSA_EINVAL
+    assert L.gsa_divsufsort(N.ptr(t), N.ptr(sa), -1) == N.GSA_EINVAL
+    assert L.gsa_divsufsort(N.ptr(t), N.ptr(sa), 0) == 0
+    assert L.gsa_divsufsort(N.ptr(t), N.ptr(sa), 1) == 0 and sa[0] == 0
+    assert L.gsa_divsufsort(N.ptr(t), N.ptr(sa), 2) == 0 and sa.tolist() == [1, 0]
+    t2 = np.frombuffer(b"ab", np.uint8)
+    assert L.gsa_divsufsort(N.ptr(t2), N.ptr(sa), 2) == 0 and sa.tolist() == [0, 1]
+    t3 = np.frombuffer(b"aa", np.uint8)
+    assert L.gsa_divsufsort(N.ptr(t3), N.ptr(sa), 2) == 0 and sa.tolist() == [1, 0]
+    h = C.c_void_p()
+    assert L.gsa_part_create(N.ptr(t), 2, 0, None, 0, C.byref(h)) == N.GSA_EPANIC  # sacapart lib.rs:43
+    assert L.gsa_build_workspace_bytes(0) == 0
+    assert L.gsa_build_workspace_bytes(1 << 20) > 33 * (1 << 20)
+
+
+def test_python_mirror_preconditions():
+    from stringsearch_b200 import divsufsort, sacapart
+
+    with pytest.raises(AssertionError, match="same len"):
+        divsufsort.sort_in_place(b"abc", np.zeros(2, np.int32))
+    sa = divsufsort.sort(b"")
+    assert sa.sa.size == 0
+    assert divsufsort.sort(b"ba").sa.tolist() == [1, 0]
+    with pytest.raises(ZeroDivisionError):
+        sacapart.PartitionedSuffixArray(b"abc", 0)
+    with pytest.raises(IndexError):
+        sa.longest_substring_match(b"x")
+
+
+def test_partition_plan_matches_oracle(port):
+    from stringsearch_b200.sacapart import partition_plan
+
+    for n in (0, 1, 2, 5, 90, 1000, 2**32):
+        for P in (1, 2, 3, 5, 8, 1001):
+            assert partition_plan(n, P) == port.part_plan(n, P)
+
+
+def test_merge_rule():
+    from stringsearch_b200.sacapart import merge_results
+
+    starts = np.array([[5, 9, 100], [50, 2, 7]], dtype=np.uint64)
+    lens = np.array([[3, 4, 4], [3, 5, 4]], dtype=np.uint32)
+    s, l = merge_results(starts, lens)
+    assert s.tolist() == [5, 2, 7] and l.tolist() == [3, 5, 4]
+
+
+def test_design_model_matches_oracle(port, sa_golden):
+    """The numpy model of the GPU scheme (tests/model_doubling.py) reproduces the oracle:
+    checks the design (packing, short suffixes, ordinal keys, discard) without a GPU."""
+    from model_doubling import build_sa_model
+
+    for name, text, sa in sa_golden:
+        if len(text) <= 1200:
+            assert build_sa_model(text).tolist() == sa.tolist(), name
+    for t in random_cases(seed=21, sizes=(3, 8, 9, 33, 65, 200)):
+        assert (build_sa_model(t) == port.sa_build(t)).all()
+
+
+def test_synth_shapes():
+    from stringsearch_b200 import synth
+
+    assert set(np.unique(synth.acgt(1000, 1)).tolist()) <= set(b"ACGT")
+    x = synth.repetitive(10_000, 3, period=100, mutation_rate=1e-2)
+    assert x.size == 10_000 and (x[:100] != x[100:200]).sum() < 20
+    flat, off = synth.patterns_from_text(synth.acgt(5000, 5), 10, 32, 6)
+    assert flat.size == 320 and off.tolist() == list(range(0, 321, 32))
