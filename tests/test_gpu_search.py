@@ -30,7 +30,7 @@ def _mixed_patterns(t: np.ndarray, rng, q, max_len):
                 b[-1] = int(alpha[rng.integers(0, alpha.size)])
             p = bytes(b)
         elif kind == 2 and n > 0:  # runs off the end of the text
-            o = int(rng.integers(max(0, n - m), n))
+            o = int(rng.integers(max(0, n - max(m, 1)), n))
             p = t[o:].tobytes() + bytes(alpha[rng.integers(0, alpha.size, int(rng.integers(0, 4)))])
         else:
             p = alpha[rng.integers(0, alpha.size, m)].tobytes() if alpha.size else b"x" * m
