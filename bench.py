@@ -272,37 +272,9 @@ def run_ours(args, rank, local_rank, world):
     # ---- end to end through the reference-facing call (host pointers) -----------------------
     del ws
     torch.cuda.empty_cache()
-    pin_t = N.PinnedBuffer(n)
-    pin_sa = N.PinnedBuffer(4 * n)
-    pin_t.array[:] = t_host
-    sa_view = pin_sa.view(np.int32, n)
-    e2e_steps = max(1, min(args.steps, 3))
-    est = N.BuildStats()
-
-    def e2e_step():
-        rc = N.lib.gsa_divsufsort_ex(pin_t.array.ctypes.data, sa_view.ctypes.data, n, local_rank, C.byref(est))
-        if rc != 0:
-            raise RuntimeError(f"gsa_divsufsort_ex rc={rc}: {N.last_error()}")
-
-    e2e_step()  # warm-up
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_step()
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    t_e = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
-    e2e_value = world * n * e2e_steps / float(t_e.item()) / MB
-    e2e_same = bool((torch.from_numpy(sa_view[: 1 << 20].copy()).to(dev) == d_sa[: 1 << 20]).all().item())
-    if not e2e_same:
-        raise RuntimeError("bench: e2e SA differs from the device-resident SA")
-    e2e = {"value": e2e_value, "unit": "MB/s", "h2d_bytes_per_step": n, "d2h_bytes_per_step": 4 * n,
-           "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3, "ms_h2d": est.ms_h2d, "ms_d2h": est.ms_d2h,
-           "ms_build": est.ms_total, "api": "gsa_divsufsort_ex(host T, host SA) with pinned buffers, workspace allocated per call"}
-    pin_t.free()
-    pin_sa.free()
+    e2e = None
+    if args.e2e:
+        e2e = run_e2e(args, N, torch, dist, dev, local_rank, world, t_host, d_sa, n, barrier)
 
     if rank != 0:
         if world > 1:
@@ -350,6 +322,41 @@ def run_ours(args, rank, local_rank, world):
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def run_e2e(args, N, torch, dist, dev, local_rank, world, t_host, d_sa, n, barrier):
+    pin_t = N.PinnedBuffer(n)
+    pin_sa = N.PinnedBuffer(4 * n)
+    pin_t.array[:] = t_host
+    sa_view = pin_sa.view(np.int32, n)
+    e2e_steps = max(1, min(args.steps, 3))
+    est = N.BuildStats()
+
+    def e2e_step():
+        rc = N.lib.gsa_divsufsort_ex(pin_t.array.ctypes.data, sa_view.ctypes.data, n, local_rank, C.byref(est))
+        if rc != 0:
+            raise RuntimeError(f"gsa_divsufsort_ex rc={rc}: {N.last_error()}")
+
+    e2e_step()  # warm-up
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t_e = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+    e2e_value = world * n * e2e_steps / float(t_e.item()) / MB
+    e2e_same = bool((torch.from_numpy(sa_view[: 1 << 20].copy()).to(dev) == d_sa[: 1 << 20]).all().item())
+    if not e2e_same:
+        raise RuntimeError("bench: e2e SA differs from the device-resident SA")
+    e2e = {"value": e2e_value, "unit": "MB/s", "h2d_bytes_per_step": n, "d2h_bytes_per_step": 4 * n,
+           "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3, "ms_h2d": est.ms_h2d, "ms_d2h": est.ms_d2h,
+           "ms_build": est.ms_total, "api": "gsa_divsufsort_ex(host T, host SA) with pinned host buffers; device scratch block cached between calls"}
+    pin_t.free()
+    pin_sa.free()
+    return e2e
 
 
 def bench_queries(dev, device_index):
@@ -426,6 +433,7 @@ def main():
     ap.add_argument("--workload", default="rep_1G")
     ap.add_argument("--no-queries", dest="queries", action="store_false")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    ap.add_argument("--no-e2e", dest="e2e", action="store_false", help="profiling runs only: skip the host-pointer leg")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -9,8 +9,9 @@
  * to the reference checkout).  Signatures use plain pointers and sizes only; no
  * torch / C++ types.  All functions are re-entrant and may be called from several
  * host threads at once (sacapart calls its builder from rayon workers,
- * crates/sacapart/src/lib.rs:41,45-49): there is no global mutable state, every
- * call selects its device and uses its own stream and workspace.
+ * crates/sacapart/src/lib.rs:41,45-49): every call selects its device and uses its
+ * own stream and workspace; the only shared state is a mutex-protected per-device
+ * cache of one idle scratch block (see gsa_release_cached_memory).
  *
  * Error convention: the library never aborts.  Codes follow libdivsufsort
  * (c-sources/divsufsort.c:346,359) and extend them:
@@ -204,6 +205,10 @@ int32_t gsa_index_create_shard(const uint8_t *T_full, uint64_t n_full, uint64_t 
 /* Pinned host memory for the end-to-end path (plain cudaHostAlloc / cudaFreeHost). */
 void *gsa_host_alloc(size_t bytes);
 void gsa_host_free(void *p);
+/* The host-pointer entry points keep one scratch allocation per device between calls
+ * (device text + SA + sort workspace; allocating tens of GB per call would dominate
+ * end-to-end time).  This returns all idle cached blocks to the CUDA driver. */
+void gsa_release_cached_memory(void);
 /* Thread-local text of the last CUDA/runtime error seen by this thread. */
 const char *gsa_last_error(void);
 /* Library version string, also names the compiled arch ("sm_100a"). */

@@ -114,6 +114,7 @@ def _load() -> C.CDLL:
         "gsa_part_destroy": ([vp], None),
         "gsa_host_alloc": ([C.c_size_t], vp),
         "gsa_host_free": ([vp], None),
+        "gsa_release_cached_memory": ([], None),
         "gsa_last_error": ([], C.c_char_p),
         "gsa_version": ([], C.c_char_p),
         "gsa_device_count": ([], C.c_int32),

@@ -5,6 +5,7 @@
 // All compute is in sa_build.cu / search.cu / verify.cu.  There is no CPU fallback: with
 // no usable GPU every compute entry point returns GSA_ECUDA.
 #include <algorithm>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -61,6 +62,69 @@ struct DevBuf {
   ~DevBuf() { if (p) cudaFree(p); }
 };
 
+// Per-device cache of the scratch block used by the host-pointer entry points (text + SA +
+// sort workspace).  cudaMalloc/cudaFree of tens of GB costs more than the copies they
+// bracket; the block is kept between calls and reused when it is large enough and free.
+// A concurrent call on the same device (sacapart-style threaded builders) simply allocates
+// its own block.  gsa_release_cached_memory() returns everything to the driver.
+struct ScratchCache {
+  static constexpr int kMaxDev = 64;
+  std::mutex mu;
+  char *ptr[kMaxDev] = {};
+  size_t bytes[kMaxDev] = {};
+  bool busy[kMaxDev] = {};
+} g_scratch;
+
+struct Scratch {
+  char *p = nullptr;
+  size_t bytes = 0;
+  int dev = -1;
+  bool cached = false;
+  int acquire(int device, size_t need) {
+    dev = device;
+    if (device >= 0 && device < ScratchCache::kMaxDev) {
+      std::lock_guard<std::mutex> lk(g_scratch.mu);
+      if (!g_scratch.busy[device]) {
+        if (g_scratch.bytes[device] < need) {
+          if (g_scratch.ptr[device]) cudaFree(g_scratch.ptr[device]);
+          g_scratch.ptr[device] = nullptr;
+          g_scratch.bytes[device] = 0;
+          char *np = nullptr;
+          if (cudaMalloc(&np, need) != cudaSuccess) {
+            set_error("cudaMalloc failed (scratch)", __FILE__, __LINE__);
+            cudaGetLastError();
+            return GSA_ENOMEM;
+          }
+          g_scratch.ptr[device] = np;
+          g_scratch.bytes[device] = need;
+        }
+        g_scratch.busy[device] = true;
+        p = g_scratch.ptr[device];
+        bytes = g_scratch.bytes[device];
+        cached = true;
+        return GSA_OK;
+      }
+    }
+    if (cudaMalloc(&p, need) != cudaSuccess) {
+      p = nullptr;
+      set_error("cudaMalloc failed (scratch)", __FILE__, __LINE__);
+      cudaGetLastError();
+      return GSA_ENOMEM;
+    }
+    bytes = need;
+    return GSA_OK;
+  }
+  ~Scratch() {
+    if (!p) return;
+    if (cached) {
+      std::lock_guard<std::mutex> lk(g_scratch.mu);
+      g_scratch.busy[dev] = false;
+    } else {
+      cudaFree(p);
+    }
+  }
+};
+
 int current_device() {
   int d = 0;
   if (cudaGetDevice(&d) != cudaSuccess) { cudaGetLastError(); return 0; }
@@ -103,6 +167,22 @@ int32_t gsa_device_count(void) {
   return c;
 }
 
+void gsa_release_cached_memory(void) {
+  std::lock_guard<std::mutex> lk(g_scratch.mu);
+  int prev = -1;
+  cudaGetDevice(&prev);
+  for (int d = 0; d < ScratchCache::kMaxDev; ++d) {
+    if (g_scratch.ptr[d] && !g_scratch.busy[d]) {
+      cudaSetDevice(d);
+      cudaFree(g_scratch.ptr[d]);
+      g_scratch.ptr[d] = nullptr;
+      g_scratch.bytes[d] = 0;
+    }
+  }
+  if (prev >= 0) cudaSetDevice(prev);
+  cudaGetLastError();
+}
+
 void *gsa_host_alloc(size_t bytes) {
   void *p = nullptr;
   if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
@@ -135,22 +215,26 @@ int32_t gsa_divsufsort_ex(const uint8_t *T, int32_t *SA, int32_t n, int32_t devi
   if (!dg.ok) return GSA_ECUDA;
   Stream st;
   GSA_TRY_RC(st.create());
-  DevBuf<u8> d_T;
-  DevBuf<i32> d_SA;
-  GSA_TRY_RC(d_T.alloc((size_t)n + 64));
-  GSA_TRY_RC(d_SA.alloc((size_t)n));
+  // one scratch block: [text | SA | sort workspace]
+  const size_t text_bytes = align_up((size_t)n + 64, 256), sa_bytes = align_up((size_t)n * sizeof(i32), 256);
+  const size_t ws_bytes = build_workspace_bytes((u32)n);
+  Scratch sc;
+  GSA_TRY_RC(sc.acquire(device, text_bytes + sa_bytes + ws_bytes));
+  u8 *d_T = reinterpret_cast<u8 *>(sc.p);
+  i32 *d_SA = reinterpret_cast<i32 *>(sc.p + text_bytes);
+  void *d_ws = sc.p + text_bytes + sa_bytes;
   cudaEvent_t e0, e1, e2, e3;
   GSA_TRY(cudaEventCreate(&e0)); GSA_TRY(cudaEventCreate(&e1));
   GSA_TRY(cudaEventCreate(&e2)); GSA_TRY(cudaEventCreate(&e3));
   struct EvFree { cudaEvent_t a, b, c, d; ~EvFree() { cudaEventDestroy(a); cudaEventDestroy(b); cudaEventDestroy(c); cudaEventDestroy(d); } } evg{e0, e1, e2, e3};
   GSA_TRY(cudaEventRecord(e0, st.s));
-  GSA_TRY(cudaMemcpyAsync(d_T.p, T, (size_t)n, cudaMemcpyHostToDevice, st.s));
+  GSA_TRY(cudaMemcpyAsync(d_T, T, (size_t)n, cudaMemcpyHostToDevice, st.s));
   GSA_TRY(cudaEventRecord(e1, st.s));
   gsa_build_stats local;
   gsa_build_stats *sp = stats ? stats : &local;
-  GSA_TRY_RC(build_sa_device(d_T.p, d_SA.p, (u32)n, nullptr, 0, st.s, sp));
+  GSA_TRY_RC(build_sa_device(d_T, d_SA, (u32)n, d_ws, ws_bytes, st.s, sp));
   GSA_TRY(cudaEventRecord(e2, st.s));
-  GSA_TRY(cudaMemcpyAsync(SA, d_SA.p, (size_t)n * sizeof(i32), cudaMemcpyDeviceToHost, st.s));
+  GSA_TRY(cudaMemcpyAsync(SA, d_SA, (size_t)n * sizeof(i32), cudaMemcpyDeviceToHost, st.s));
   GSA_TRY(cudaEventRecord(e3, st.s));
   GSA_TRY(cudaStreamSynchronize(st.s));
   cudaEventElapsedTime(&sp->ms_h2d, e0, e1);

@@ -1,12 +1,12 @@
 // radix.cuh -- hand-written LSD radix sort building blocks for (u64 key, u32 value)
 // pairs on sm_100a.  No CUB / Thrust.
 //
-//   hist_add()          warp-aggregated multi-digit histogram update (match.any on the
-//                       whole key, one shared-memory atomic per digit per distinct key)
+//   hist_add()          warp-aggregated multi-digit histogram update (runs of equal adjacent
+//                       keys are added once, by ballot; no match.any)
 //   k_scan_hist         per-digit exclusive scan of the global histograms + detection
 //                       of constant digits (their pass is skipped by the host)
 //   k_radix_pass        one "onesweep" pass: a tile is ranked in shared memory with
-//                       warp match.any, its per-digit counts are chained to the
+//                       warp ballots / match.any, its per-digit counts are chained to the
 //                       preceding tiles by a decoupled look-back, and keys/values are
 //                       scattered in digit runs.  Optionally generates the round-0 keys
 //                       on the fly from the bit-packed text (GEN) so they are never
@@ -54,18 +54,24 @@ __device__ __forceinline__ void gen_key0(const KeyGen &g, u32 j, u64 &key, u32 &
 }
 
 // Warp-aggregated histogram update for `npass` 8-bit digits of `key` (digit p = bits
-// [8p, 8p+8)).  Lanes holding the same key elect a leader which adds the multiplicity
-// once per digit, so runs of identical keys (the common case in doubling rounds) do
-// not serialise on one shared-memory address.  Must be called by all lanes of the warp
-// (valid = false for lanes without an element).
+// [8p, 8p+8)).  Lanes hold consecutive elements; a run of equal adjacent keys (the common
+// case in doubling rounds, where most of a group shares one key) is added once by its first
+// lane with the run length, so it does not serialise on one shared-memory address.  Distinct
+// neighbours cost two shuffles and a ballot -- no match.any, whose latency grows with the
+// number of distinct values in the warp (ncu: 150+ cycles on random keys).
+// Must be called by all lanes of the warp; valid lanes must form a prefix of the warp.
 __device__ __forceinline__ void hist_add(u32 *shist, u64 key, bool valid, int npass) {
-  const u32 act = __ballot_sync(0xffffffffu, valid);
-  if (valid) {
-    const u32 peers = __match_any_sync(act, key);
-    if (lane_id() == (u32)(31 - __clz(peers))) {
-      const u32 c = __popc(peers);
-      for (int p = 0; p < npass; ++p) atomicAdd(&shist[p * RADIX + (u32)((key >> (8 * p)) & 255u)], c);
-    }
+  const u32 lane = lane_id();
+  const u64 prev = __shfl_up_sync(0xffffffffu, key, 1);
+  const bool head = valid && (lane == 0 || prev != key);
+  const u32 heads = __ballot_sync(0xffffffffu, head);
+  const u32 nvalid = __popc(__ballot_sync(0xffffffffu, valid));
+  if (head) {
+    const u32 above = heads & ~((2u << lane) - 1u);  // run heads in higher lanes
+    const u32 end = above ? (u32)(__ffs(above) - 1) : 32u;
+    const u32 c = min(end, nvalid) - lane;
+#pragma unroll 1
+    for (int p = 0; p < npass; ++p) atomicAdd(&shist[p * RADIX + (u32)((key >> (8 * p)) & 255u)], c);
   }
 }
 
@@ -115,15 +121,29 @@ struct PassCfg {
   static constexpr size_t SMEM = (size_t)TILE * 8 + (size_t)TILE * 4 + (size_t)WARPS * RADIX * 4 + RADIX * 4 + RADIX * 4;
 };
 
+// Lanes of the warp whose 8-bit digit equals mine, from 8 ballots (cost independent of the
+// number of distinct digits in the warp).
+__device__ __forceinline__ u32 peers_by_ballot(u32 d) {
+  u32 m = 0xffffffffu;
+#pragma unroll
+  for (int b = 0; b < RADIX_BITS; ++b) {
+    const u32 bit = (d >> b) & 1u;
+    const u32 bal = __ballot_sync(0xffffffffu, bit);
+    m &= bal ^ (bit - 1u);  // bit ? bal : ~bal
+  }
+  return m;
+}
+
 template <int THREADS, int IPT, bool GEN>
-__global__ void __launch_bounds__(THREADS) k_radix_pass(const PassArgs a) {
+__global__ void __launch_bounds__(THREADS, 3) k_radix_pass(const PassArgs a) {
   static_assert(THREADS >= RADIX && THREADS % 32 == 0, "one thread per bin is assumed");
+  static_assert(IPT % 2 == 0 && 32 * IPT <= 65535, "warp-local ranks are packed as u16 pairs");
   constexpr int WARPS = THREADS / 32;
   constexpr int TILE = THREADS * IPT;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   u64 *skeys = reinterpret_cast<u64 *>(smem_raw);          // [TILE]
   u32 *svals = reinterpret_cast<u32 *>(skeys + TILE);      // [TILE]
-  u32 *whist = svals + TILE;                               // [WARPS][256] counts -> running offsets
+  u32 *whist = svals + TILE;                               // [WARPS][256] counts -> offsets
   u32 *bin_excl = whist + WARPS * RADIX;                   // [256] tile-local exclusive offset of each bin
   u32 *bin_gofs = bin_excl + RADIX;                        // [256] global offset - local offset
   __shared__ u32 s_tile;
@@ -157,13 +177,49 @@ __global__ void __launch_bounds__(THREADS) k_radix_pass(const PassArgs a) {
     }
   }
 
-  // ---- per-warp digit counts (match.any: one shared atomic per distinct digit) ---------
-  u32 m[IPT];
+  // ---- per-warp digit counts and warp-local stable ranks in one step -----------------------
+  // For each row k the lanes holding the same digit elect their lowest lane, which claims
+  // `count` slots of the warp's bin with one shared-memory atomic (with return) and hands the
+  // base to its peers; local rank = base + number of peers in lower lanes.  Rows are issued in
+  // order by the converged warp, so equal digits keep their (k, lane) order: stable.
+  // Peer masks come from match.any when the first row shows few distinct digits in the warp
+  // (match.any's cost grows with the number of distinct values) and from 8 ballots otherwise.
+  u32 lrank[IPT / 2];  // two u16 per register
+  const u32 lt = lanemask_lt();
+  u32 *wh = whist + warp * RADIX;
+  bool use_match;
+  {
+    const u32 d = (u32)(key[0] >> a.shift) & 255u;
+    const u32 peers = peers_by_ballot(d);
+    const u32 below = __popc(peers & lt);
+    u32 base = 0;
+    if (below == 0) base = atomicAdd(&wh[d], (u32)__popc(peers));
+    base = __shfl_sync(0xffffffffu, base, __ffs(peers) - 1);
+    lrank[0] = base + below;
+    use_match = __popc(__ballot_sync(0xffffffffu, below == 0)) <= 6;
+  }
+  if (use_match) {
 #pragma unroll
-  for (int k = 0; k < IPT; ++k) {
-    const u32 d = (u32)(key[k] >> a.shift) & 255u;
-    m[k] = __match_any_sync(0xffffffffu, d);
-    if (lane == 31 - __clz(m[k])) atomicAdd(&whist[warp * RADIX + d], (u32)__popc(m[k]));
+    for (int k = 1; k < IPT; ++k) {
+      const u32 d = (u32)(key[k] >> a.shift) & 255u;
+      const u32 peers = __match_any_sync(0xffffffffu, d);
+      const u32 below = __popc(peers & lt);
+      u32 base = 0;
+      if (below == 0) base = atomicAdd(&wh[d], (u32)__popc(peers));
+      base = __shfl_sync(0xffffffffu, base, __ffs(peers) - 1);
+      if (k & 1) lrank[k >> 1] |= (base + below) << 16; else lrank[k >> 1] = base + below;
+    }
+  } else {
+#pragma unroll
+    for (int k = 1; k < IPT; ++k) {
+      const u32 d = (u32)(key[k] >> a.shift) & 255u;
+      const u32 peers = peers_by_ballot(d);
+      const u32 below = __popc(peers & lt);
+      u32 base = 0;
+      if (below == 0) base = atomicAdd(&wh[d], (u32)__popc(peers));
+      base = __shfl_sync(0xffffffffu, base, __ffs(peers) - 1);
+      if (k & 1) lrank[k >> 1] |= (base + below) << 16; else lrank[k >> 1] = base + below;
+    }
   }
   __syncthreads();
 
@@ -201,35 +257,38 @@ __global__ void __launch_bounds__(THREADS) k_radix_pass(const PassArgs a) {
   }
   __syncthreads();
 
-  // ---- rank inside the tile (stable) and stage in shared memory -------------------------
-  const u32 lt = lanemask_lt();
+  // ---- final rank inside the tile; stage in shared memory ---------------------------------
 #pragma unroll
   for (int k = 0; k < IPT; ++k) {
     const u32 d = (u32)(key[k] >> a.shift) & 255u;
-    const u32 peers = m[k];
-    const u32 base = whist[warp * RADIX + d];
-    __syncwarp();
-    if (lane == 31 - __clz(peers)) whist[warp * RADIX + d] = base + (u32)__popc(peers);
-    __syncwarp();
-    m[k] = base + (u32)__popc(peers & lt);
-  }
-#pragma unroll
-  for (int k = 0; k < IPT; ++k) {
-    skeys[m[k]] = key[k];
-    svals[m[k]] = val[k];
+    const u32 r = wh[d] + ((k & 1) ? (lrank[k >> 1] >> 16) : (lrank[k >> 1] & 0xffffu));
+    skeys[r] = key[k];
+    svals[r] = val[k];
   }
 
-  // ---- decoupled look-back: one thread per bin ------------------------------------------
+  // ---- decoupled look-back: one thread per bin, four predecessors per round trip ------------
   if (tid < RADIX) {
     u32 excl = 0;
     if (tile != 0) {
-      const u32 *st = a.status + (size_t)(tile - 1) * RADIX + tid;
+      const u32 *base = a.status + tid;
+      i64 t = (i64)tile - 1;
+      const u32 done0 = st_pre(0);  // virtual tiles in front of tile 0
       for (;;) {
-        u32 s;
-        do { s = ld_volatile_u32(st); } while (s == 0u);
-        excl += (s & 0x7fffffffu) - 1u;
-        if (s & 0x80000000u) break;
-        st -= RADIX;
+        u32 s[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) s[j] = (t - j >= 0) ? ld_volatile_u32(base + (size_t)(t - j) * RADIX) : done0;
+        int used = 0;
+        bool fin = false;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (!fin && used == j && s[j] != 0u) {
+            excl += (s[j] & 0x7fffffffu) - 1u;
+            used = j + 1;
+            fin = (s[j] & 0x80000000u) != 0u;
+          }
+        }
+        if (fin) break;
+        t -= used;  // used == 0: the nearest predecessor is not ready yet, poll again
       }
       st_volatile_u32(a.status + (size_t)tile * RADIX + tid, st_pre(excl + pub));
     }

@@ -16,6 +16,8 @@
 //   pos u32[n] x2 (SA slot of each live element)   ord u32[n] (group ordinal)
 //   rank u32[n]   SA i32[n] (caller's)   + histogram / look-back status scratch.
 #include "builder.h"
+#include <stdlib.h>
+
 #include <algorithm>
 #include <vector>
 
@@ -149,9 +151,7 @@ struct RebuildArgs {
   u32 *pos_out;
   u32 *sufx_out;
   u32 *ord_out;
-  u64 *statusA;        // [tiles] flag(2) | head+1
-  u64 *statusB;        // [tiles] flag(2) | survivors(31) | groups(31)
-  u32 *counter;
+  ulonglong2 *status;  // [tiles] x = flag(2) | head+1 ; y = flag(2) | survivors(31) | groups(31)
   RoundResult *result;
 };
 
@@ -159,17 +159,28 @@ constexpr u64 ST_AGG = 1ull << 62;
 constexpr u64 ST_PRE = 2ull << 62;
 constexpr u64 ST_FLAG = 3ull << 62;
 
+// One 16-byte, 16-byte-aligned access per tile descriptor (a single memory transaction on
+// the hardware).  Both halves carry the state flag, so a torn read -- should one ever
+// happen -- is seen as "flags differ" and simply retried.
+__device__ __forceinline__ ulonglong2 ld_status(const ulonglong2 *p) {
+  ulonglong2 v;
+  asm volatile("ld.volatile.global.v2.u64 {%0,%1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_status(ulonglong2 *p, u64 x, u64 y) {
+  asm volatile("st.volatile.global.v2.u64 [%0], {%1,%2};" ::"l"(p), "l"(x), "l"(y) : "memory");
+}
+
 template <int THREADS, int IPT, bool ROUND0>
 __global__ void __launch_bounds__(THREADS) k_rebuild(const RebuildArgs a) {
   constexpr int WARPS = THREADS / 32;
   constexpr int TILE = THREADS * IPT;
-  __shared__ u32 s_tile;
   __shared__ u32 s_wh[WARPS], s_wc[WARPS], s_wg[WARPS];
   __shared__ u32 s_pre[3];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) s_tile = atomicAdd(a.counter, 1u);
-  __syncthreads();
-  const u32 tile = s_tile;
+  // Tiles are taken in blockIdx order: the look-back only ever waits on lower-numbered
+  // blocks, which the hardware dispatches first.
+  const u32 tile = blockIdx.x;
   const u32 L = a.L;
   const u32 l0 = tile * (u32)TILE + (u32)tid * IPT;
 
@@ -265,39 +276,26 @@ __global__ void __launch_bounds__(THREADS) k_rebuild(const RebuildArgs a) {
     eh = max(eh, ph); ec += pc; eg += pg;
   }
 
-  // ---- tile prefix by decoupled look-back (warp 0) -----------------------------------------
+  // ---- tile prefix by decoupled look-back (warp 0, 32 predecessors per round trip) ----------
   if (warp == 0) {
     u32 xh = 0, xc = 0, xg = 0;  // exclusive prefix over preceding tiles
     if (tile == 0) {
-      if (lane == 0) {
-        st_volatile_u64(a.statusA, ST_PRE | bh);
-        st_volatile_u64(a.statusB, ST_PRE | ((u64)bc << 31) | bg);
-      }
+      if (lane == 0) st_status(a.status, ST_PRE | bh, ST_PRE | ((u64)bc << 31) | bg);
     } else {
-      if (lane == 0) {
-        st_volatile_u64(a.statusA + tile, ST_AGG | bh);
-        st_volatile_u64(a.statusB + tile, ST_AGG | ((u64)bc << 31) | bg);
-      }
+      if (lane == 0) st_status(a.status + tile, ST_AGG | bh, ST_AGG | ((u64)bc << 31) | bg);
       i64 look = (i64)tile - 1 - lane;  // lane 0 inspects the nearest predecessor
       for (;;) {
-        u64 sa = ST_PRE, sb = ST_PRE;   // virtual tiles before tile 0: identity prefix
+        ulonglong2 sv = make_ulonglong2(ST_PRE, ST_PRE);  // virtual tiles before tile 0: identity prefix
         if (look >= 0) {
-          do { sa = ld_volatile_u64(a.statusA + look); } while ((sa & ST_FLAG) == 0);
-          do { sb = ld_volatile_u64(a.statusB + look); } while ((sb & ST_FLAG) == 0);
-          // A and B are published independently; a tile may show PREFIX in one word and still
-          // AGGREGATE in the other.  Re-read until both agree (the writer stores them back to back).
-          while ((sa & ST_FLAG) != (sb & ST_FLAG)) {
-            sa = ld_volatile_u64(a.statusA + look);
-            sb = ld_volatile_u64(a.statusB + look);
-          }
+          do { sv = ld_status(a.status + look); } while ((sv.x & ST_FLAG) == 0 || (sv.x & ST_FLAG) != (sv.y & ST_FLAG));
         }
-        const u32 pre = __ballot_sync(0xffffffffu, (sa & ST_FLAG) == ST_PRE);
+        const u32 pre = __ballot_sync(0xffffffffu, (sv.x & ST_FLAG) == ST_PRE);
         const int first = pre ? (__ffs(pre) - 1) : 32;  // nearest tile holding an inclusive prefix
         u32 vh = 0, vc = 0, vg = 0;
         if (lane <= first) {
-          vh = (u32)(sa & 0xffffffffull);
-          vc = (u32)((sb >> 31) & 0x7fffffffull);
-          vg = (u32)(sb & 0x7fffffffull);
+          vh = (u32)(sv.x & 0xffffffffull);
+          vc = (u32)((sv.y >> 31) & 0x7fffffffull);
+          vg = (u32)(sv.y & 0x7fffffffull);
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -309,10 +307,7 @@ __global__ void __launch_bounds__(THREADS) k_rebuild(const RebuildArgs a) {
         if (pre) break;
         look -= 32;
       }
-      if (lane == 0) {
-        st_volatile_u64(a.statusA + tile, ST_PRE | max(xh, bh));
-        st_volatile_u64(a.statusB + tile, ST_PRE | ((u64)(xc + bc) << 31) | (xg + bg));
-      }
+      if (lane == 0) st_status(a.status + tile, ST_PRE | max(xh, bh), ST_PRE | ((u64)(xc + bc) << 31) | (xg + bg));
     }
     if (lane == 0) {
       s_pre[0] = xh; s_pre[1] = xc; s_pre[2] = xg;
@@ -355,7 +350,7 @@ namespace {
 constexpr int PASS_THREADS = 256;
 constexpr int PASS_IPT = 16;
 constexpr int PASS_TILE = PASS_THREADS * PASS_IPT;
-constexpr int RB_THREADS = 256;
+constexpr int RB_THREADS = 512;
 constexpr int RB_IPT = 8;
 constexpr int RB_TILE = RB_THREADS * RB_IPT;
 constexpr int HIST_THREADS = 512;
@@ -380,7 +375,7 @@ struct Layout {
   u32 *skip_mask;  // [1]
   RoundResult *result;
   u32 *pass_status; size_t pass_status_words;  // counter at word 0 (256-word header), then [tiles][256]
-  u64 *rb_status; size_t rb_status_words;      // counter (u64 slot 0..31 header), A[tiles], B[tiles]
+  ulonglong2 *rb_status; size_t rb_status_words;  // one 16-byte descriptor per rebuild tile
   size_t total;
 };
 
@@ -404,8 +399,8 @@ Layout make_layout(char *base, u32 n) {
   y.pass_status_words = 256 + ptiles * RADIX;
   y.pass_status = c.take<u32>(y.pass_status_words);
   const size_t rtiles = div_up(N, RB_TILE);
-  y.rb_status_words = 32 + 2 * rtiles;
-  y.rb_status = c.take<u64>(y.rb_status_words);
+  y.rb_status_words = rtiles + 1;
+  y.rb_status = c.take<ulonglong2>(y.rb_status_words);
   y.total = c.used;
   return y;
 }
@@ -536,6 +531,22 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
     GSA_TRY(cudaGetDevice(&dev));
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   }
+  // The rank gather / scatter of the doubling rounds touches 4 bytes per 32-byte sector at
+  // random; ask L2 not to widen those misses to 64/128-byte DRAM fetches (ncu: 126 B of DRAM
+  // read per gathered rank at the default setting).  Restored before returning.
+  struct L2Fetch {
+    size_t old = 0;
+    bool changed = false;
+    L2Fetch() {
+      const char *e = getenv("GSA_L2_FETCH");
+      const size_t want = e ? (size_t)atoi(e) : 32;
+      if (want == 0) return;  // GSA_L2_FETCH=0: leave the device setting alone
+      if (cudaDeviceGetLimit(&old, cudaLimitMaxL2FetchGranularity) != cudaSuccess) { cudaGetLastError(); return; }
+      if (old != want && cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, want) == cudaSuccess) changed = true;
+      else cudaGetLastError();
+    }
+    ~L2Fetch() { if (changed) { cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, old); cudaGetLastError(); } }
+  } l2fetch_guard;
   cudaEvent_t ev[4];
   for (auto &e : ev) GSA_TRY(cudaEventCreate(&e));
   struct EvFree { cudaEvent_t *e; ~EvFree() { for (int i = 0; i < 4; ++i) cudaEventDestroy(e[i]); } } ev_guard{ev};
@@ -593,7 +604,7 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
 
   auto launch_rebuild = [&](bool round0, u32 L, int kv, int pin, int pout) -> int {
     const u32 tiles = (u32)div_up(L, RB_TILE);
-    GSA_TRY(cudaMemsetAsync(y.rb_status, 0, (32 + 2 * (size_t)tiles) * sizeof(u64), st));
+    GSA_TRY(cudaMemsetAsync(y.rb_status, 0, (size_t)tiles * sizeof(ulonglong2), st));
     RebuildArgs r;
     r.keys = y.keys[kv]; r.sufx = y.vals[kv];
     r.pos_in = round0 ? nullptr : y.pos[pin];
@@ -601,8 +612,7 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
     r.short_from = round0 ? (n - ns) : 0xffffffffu;
     r.rank = y.rank; r.SA = d_SA;
     r.pos_out = y.pos[pout]; r.sufx_out = y.vals[kv ^ 1]; r.ord_out = y.ord;
-    r.counter = reinterpret_cast<u32 *>(y.rb_status);
-    r.statusA = y.rb_status + 32; r.statusB = y.rb_status + 32 + tiles;
+    r.status = y.rb_status;
     r.result = y.result;
     if (round0)
       k_rebuild<RB_THREADS, RB_IPT, true><<<tiles, RB_THREADS, 0, st>>>(r);
