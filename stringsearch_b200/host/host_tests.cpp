@@ -48,7 +48,8 @@ int main() {
     sa.verify();
     const std::vector<int32_t> expect = {4, 8, 10, 2, 3, 9, 6, 7, 12, 1, 11, 0, 5};
     CHECK(sa.sa() == expect);
-    auto b = divsufsort::sort(std::string("banana"));
+    const std::string banana = "banana";  // the SuffixArray borrows its text (&'a [u8])
+    auto b = divsufsort::sort(banana);
     CHECK((b.search_all("ana") == std::vector<int32_t>{3, 1}));
     CHECK(b.contains("nan") && !b.contains("nab"));
   }
