@@ -1,0 +1,23 @@
+// Counterpart of crates/cdivsufsort/build.rs:1-29: instead of four C files, compile the four
+// CUDA translation units of libgsa for sm_100a through the cc crate.
+fn main() {
+    let csrc = "../../stringsearch_b200/csrc";
+    let mut build = cc::Build::new();
+    build
+        .cuda(true)
+        .cudart("static")
+        .flag("-gencode")
+        .flag("arch=compute_100a,code=sm_100a")
+        .flag("-std=c++17")
+        .flag("-O3")
+        .flag("-lineinfo")
+        .flag("-rdc=true")
+        .include("../../include")
+        .warnings(false);
+    for f in &["api.cu", "sa_build.cu", "search.cu", "verify.cu"] {
+        build.file(format!("{}/{}", csrc, f));
+        println!("cargo:rerun-if-changed={}/{}", csrc, f);
+    }
+    build.compile("libgsa.a");
+    println!("cargo:rustc-link-lib=stdc++");
+}

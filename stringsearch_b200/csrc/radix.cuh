@@ -54,22 +54,23 @@ __device__ __forceinline__ void gen_key0(const KeyGen &g, u32 j, u64 &key, u32 &
 }
 
 // Warp-aggregated histogram update for `npass` 8-bit digits of `key` (digit p = bits
-// [8p, 8p+8)).  Lanes hold consecutive elements; a run of equal adjacent keys (the common
-// case in doubling rounds, where most of a group shares one key) is added once by its first
-// lane with the run length, so it does not serialise on one shared-memory address.  Distinct
-// neighbours cost two shuffles and a ballot -- no match.any, whose latency grows with the
-// number of distinct values in the warp (ncu: 150+ cycles on random keys).
-// Must be called by all lanes of the warp; valid lanes must form a prefix of the warp.
+// [8p, 8p+8)).  Lanes hold consecutive elements; a run of equal adjacent keys in valid lanes
+// (the common case in doubling rounds, where most of a group shares one key) is added once
+// by its first lane with the run length, so it does not serialise on one shared-memory
+// address.  Distinct neighbours cost a shuffle and two ballots -- no match.any, whose latency
+// grows with the number of distinct values in the warp (ncu: 150+ cycles on random keys).
+// Must be called by all lanes of the warp.
 __device__ __forceinline__ void hist_add(u32 *shist, u64 key, bool valid, int npass) {
   const u32 lane = lane_id();
   const u64 prev = __shfl_up_sync(0xffffffffu, key, 1);
-  const bool head = valid && (lane == 0 || prev != key);
+  const u32 vmask = __ballot_sync(0xffffffffu, valid);
+  const bool pvalid = lane > 0 && ((vmask >> (lane - 1)) & 1u);
+  const bool head = valid && (!pvalid || prev != key);
   const u32 heads = __ballot_sync(0xffffffffu, head);
-  const u32 nvalid = __popc(__ballot_sync(0xffffffffu, valid));
   if (head) {
-    const u32 above = heads & ~((2u << lane) - 1u);  // run heads in higher lanes
-    const u32 end = above ? (u32)(__ffs(above) - 1) : 32u;
-    const u32 c = min(end, nvalid) - lane;
+    const u32 hi = ~((2u << lane) - 1u);       // lanes above mine
+    const u32 stop = (heads | ~vmask) & hi;    // next run head or next empty lane
+    const u32 c = (stop ? (u32)(__ffs(stop) - 1) : 32u) - lane;
 #pragma unroll 1
     for (int p = 0; p < npass; ++p) atomicAdd(&shist[p * RADIX + (u32)((key >> (8 * p)) & 255u)], c);
   }

@@ -5,16 +5,26 @@
 // reproduced.
 //
 // Round 0   text bytes -> dense codes (b bits) -> bit-packed stream; key(i) = the next
-//           k = floor(64/b) symbols of suffix i, zero padded; LSD radix sort of
-//           (key, i); adjacent-key-differs flags + scan give group heads;
-//           rank[i] = head slot + 1 (0 is the end-of-text sentinel).
-// Round r   live (not yet unique) suffixes only: key = (group ordinal, rank[i + h]);
-//           sort, re-flag, re-rank, finalise singletons into SA, compact the rest.
+//           k = floor(64/b) symbols of suffix i, zero padded; LSD radix sort of (key, i);
+//           adjacent-key-differs flags + head/tail scans give every group's slot range.
+// Round r   live (not yet unique) suffixes only, walked in text order so that the two rank
+//           reads per suffix are coalesced: key = (rank[i], rank[i + h]); sort, re-flag,
+//           finalise singletons into SA, compact the surviving slots.
+//
+// rank[i] is a *label* of i's group: some SA slot inside the group's slot range, plus one
+// (0 = "past the end of the text", bit 31 = suffix finalised).  Ranges of different groups
+// are disjoint and ordered, so labels order groups correctly, and a group KEEPS its label
+// for as long as the label stays inside its shrinking range.  Only suffixes whose group
+// gets a new label (the middle of the new range) or that become unique are written -- the
+// random 4-byte scatter is the most expensive memory operation of a round (22-27 G/s on
+// B200 whatever the store flavour, tools/ubench/gather_scatter.cu), and with slot-of-head
+// ranks nearly every suffix of a repetitive text would be rewritten in every round.
 //
 // Data layout in HBM (n = text length, L = live suffixes, all arrays contiguous):
 //   packed  u64[n*b/64 + 2]   keys u64[n] x2   vals(suffix) u32[n] x2
-//   pos u32[n] x2 (SA slot of each live element)   ord u32[n] (group ordinal)
-//   rank u32[n]   SA i32[n] (caller's)   + histogram / look-back status scratch.
+//   pos u32[n] x2 (SA slot of each live element, SA order)
+//   lst u32[n] x2 (live suffixes, text order)   rank u32[n]   SA i32[n] (caller's)
+//   + histograms, pass / rebuild look-back descriptors, per-tile tail summaries.
 #include "builder.h"
 #include <stdlib.h>
 
@@ -100,45 +110,117 @@ __global__ void __launch_bounds__(THREADS) k_hist0(const KeyGen g, int npass, u3
     if (shist[i]) atomicAdd(&ghist[i], shist[i]);
 }
 
-// Rounds >= 1: build the sort key of every live suffix and histogram its digits.
-//   key = (ordinal of the suffix's group among live groups) << rank_bits | rank[i + h]
-//   (rank 0 = "i + h is past the end", which sorts first: a proper prefix is smaller).
-template <int THREADS>
-__global__ void __launch_bounds__(THREADS) k_gather_hist(const u32 *__restrict__ sufx, const u32 *__restrict__ ord,
-                                                         const u32 *__restrict__ rank, u64 *__restrict__ keys, u32 L,
-                                                         u32 n, u64 h, u32 rank_bits, int npass,
-                                                         u32 *__restrict__ ghist) {
+// ------------------------------------------------------------------------------------
+// Rounds >= 1, step 1: walk the candidate suffixes in text order, drop the finalised ones,
+// build the sort key of the live ones, histogram its digits, and emit
+//   (key, suffix) -> sort input,   suffix -> next round's candidate list.
+//   key = label(i) << lab_bits | label(i + h)     (0 when i + h is past the end: a proper
+//                                                  prefix sorts first)
+// Consecutive candidates are consecutive in the text (up to a permutation of 4096-element
+// chunks), so rank[i] and rank[i + h] are streamed, not gathered.  Output slots come from one
+// atomicAdd per chunk; the order of the sort input does not matter.
+// ------------------------------------------------------------------------------------
+constexpr u32 RANK_DEAD = 0x80000000u;
+constexpr u32 RANK_MASK = 0x7fffffffu;
+
+struct GatherArgs {
+  const u32 *lst_in;  // null: candidates are 0..Lin-1
+  u32 Lin;
+  const u32 *rank;
+  u32 n;
+  u64 h;
+  u32 lab_bits;
+  int npass;
+  u64 *keys_out;
+  u32 *vals_out;
+  u32 *lst_out;
+  u32 *counter;  // zeroed before launch; ends at the number of live suffixes
+  u32 *ghist;
+};
+
+template <int THREADS, int IPT>
+__global__ void __launch_bounds__(THREADS) k_gather(const GatherArgs a) {
+  constexpr int WARPS = THREADS / 32;
+  constexpr u32 CH = THREADS * IPT;
   __shared__ u32 shist[MAX_PASSES * RADIX];
-  for (int i = threadIdx.x; i < npass * RADIX; i += THREADS) shist[i] = 0;
+  __shared__ u32 s_wcnt[WARPS];
+  __shared__ u32 s_base;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < a.npass * RADIX; i += THREADS) shist[i] = 0;
   __syncthreads();
-  const u32 stride = gridDim.x * THREADS;
-  const u32 iters = (L + stride - 1) / stride;
-  u32 l = blockIdx.x * THREADS + threadIdx.x;
-  for (u32 it = 0; it < iters; ++it, l += stride) {
-    const bool valid = l < L;
-    u64 key = 0;
-    if (valid) {
-      const u64 t = (u64)ld_stream_u32(sufx + l) + h;
-      const u32 r2 = (t < n) ? __ldg(rank + t) : 0u;
-      key = ((u64)ld_stream_u32(ord + l) << rank_bits) | r2;
-      keys[l] = key;
+  const u32 lt = lanemask_lt();
+  const u32 nchunks = (a.Lin + CH - 1) / CH;
+  for (u32 chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+    // warp w owns the contiguous sub-chunk [w*32*IPT, (w+1)*32*IPT); row k = 32 consecutive candidates
+    const u32 wb = chunk * CH + (u32)warp * (32u * IPT) + (u32)lane;
+    u32 sfx[IPT];
+    u64 key[IPT];
+    u32 off[IPT];  // slot offset inside the warp's output run
+    bool live[IPT];
+    u32 wtot = 0;
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) {
+      const u32 c = wb + (u32)k * 32u;
+      bool lv = false;
+      u32 i = 0, w = 0;
+      if (c < a.Lin) {
+        i = a.lst_in ? ld_stream_u32(a.lst_in + c) : c;
+        w = __ldg(a.rank + i);
+        lv = (w & RANK_DEAD) == 0u;
+      }
+      u64 kx = 0;
+      if (lv) {
+        const u64 t = (u64)i + a.h;
+        const u32 r2 = (t < a.n) ? (__ldg(a.rank + t) & RANK_MASK) : 0u;
+        kx = ((u64)w << a.lab_bits) | r2;
+      }
+      const u32 m = __ballot_sync(0xffffffffu, lv);
+      sfx[k] = i; key[k] = kx; live[k] = lv;
+      off[k] = wtot + (u32)__popc(m & lt);
+      wtot += (u32)__popc(m);
+      hist_add(shist, kx, lv, a.npass);
     }
-    hist_add(shist, key, valid, npass);
+    if (lane == 0) s_wcnt[warp] = wtot;
+    __syncthreads();
+    if (tid == 0) {
+      u32 tot = 0;
+#pragma unroll
+      for (int w = 0; w < WARPS; ++w) { const u32 c = s_wcnt[w]; s_wcnt[w] = tot; tot += c; }
+      s_base = tot ? atomicAdd(a.counter, tot) : 0u;
+    }
+    __syncthreads();
+    const u32 base = s_base + s_wcnt[warp];
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) {
+      if (live[k]) {
+        const u32 o = base + off[k];
+        a.keys_out[o] = key[k];
+        a.vals_out[o] = sfx[k];
+        a.lst_out[o] = sfx[k];
+      }
+    }
+    __syncthreads();  // s_wcnt / s_base are reused by the next chunk
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < npass * RADIX; i += THREADS)
-    if (shist[i]) atomicAdd(&ghist[i], shist[i]);
+  for (int i = tid; i < a.npass * RADIX; i += THREADS)
+    if (shist[i]) atomicAdd(&a.ghist[i], shist[i]);
 }
 
 // ------------------------------------------------------------------------------------
-// Rank rebuild + singleton finalisation + live-set compaction, one pass, chained scan.
-//   flag[l]  = key[l] != key[l-1]            (round 0: also around short suffixes)
-//   head[l]  = SA slot of the nearest flagged element at or before l   (max-scan)
-//   rank[suffix[l]] = head[l] + 1
-//   singleton (flag[l] && flag[l+1])  -> SA[pos[l]] = suffix[l], dropped from the live set
-//   otherwise -> appended to the next live set with its slot and its group's ordinal
-// Tile prefix (head, survivors, surviving groups) travels through a decoupled look-back
-// over two self-validating 64-bit status words per tile.
+// Step 3 (after the sort): re-flag, re-label, finalise, compact.  Sorted live elements l
+// (key[l], suffix[l]) sit in SA slots pos[l] (ascending).  With
+//   flag[l] = key[l] != key[l-1]           (round 0: also around short suffixes)
+//   head[l] = slot of the nearest flagged element at or before l      (forward max-scan)
+//   tail[l] = slot of the nearest element at or after l whose successor is flagged
+//                                                                      (backward min-scan)
+// the new group of l occupies slots [head, tail]:
+//   head == tail       -> unique: SA[head] = suffix, rank[suffix] = DEAD | head+1
+//   old label in range -> nothing to write (the group keeps its label)
+//   otherwise          -> rank[suffix] = middle of the range + 1
+// and the slots of the non-unique elements are compacted for the next round.
+// The forward prefix (head, survivors, groups) travels through a decoupled look-back over
+// 16-byte tile descriptors; the backward one cannot wait on later tiles, so a first light
+// kernel records every tile's first tail slot and a one-block suffix-min scan turns that
+// into "first tail slot after tile t".
 // ------------------------------------------------------------------------------------
 struct RebuildArgs {
   const u64 *keys;
@@ -146,15 +228,17 @@ struct RebuildArgs {
   const u32 *pos_in;   // null in round 0 (slot == index)
   u32 L;
   u32 short_from;      // round 0: suffix indices >= short_from are short (forced singletons)
+  u32 lab_bits;        // old label = key >> lab_bits (rounds >= 1)
   u32 *rank;
   i32 *SA;
   u32 *pos_out;
-  u32 *sufx_out;
-  u32 *ord_out;
   ulonglong2 *status;  // [tiles] x = flag(2) | head+1 ; y = flag(2) | survivors(31) | groups(31)
+  u32 *tile_tail;      // [tiles] k_tail_summary: first tail slot inside the tile (or NO_TAIL)
+  const u32 *next_tail;  // [tiles] k_tail_scan: first tail slot in any later tile
   RoundResult *result;
 };
 
+constexpr u32 NO_TAIL = 0xffffffffu;
 constexpr u64 ST_AGG = 1ull << 62;
 constexpr u64 ST_PRE = 2ull << 62;
 constexpr u64 ST_FLAG = 3ull << 62;
@@ -171,23 +255,12 @@ __device__ __forceinline__ void st_status(ulonglong2 *p, u64 x, u64 y) {
   asm volatile("st.volatile.global.v2.u64 [%0], {%1,%2};" ::"l"(p), "l"(x), "l"(y) : "memory");
 }
 
-template <int THREADS, int IPT, bool ROUND0>
-__global__ void __launch_bounds__(THREADS) k_rebuild(const RebuildArgs a) {
-  constexpr int WARPS = THREADS / 32;
-  constexpr int TILE = THREADS * IPT;
-  __shared__ u32 s_wh[WARPS], s_wc[WARPS], s_wg[WARPS];
-  __shared__ u32 s_pre[3];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  // Tiles are taken in blockIdx order: the look-back only ever waits on lower-numbered
-  // blocks, which the hardware dispatches first.
-  const u32 tile = blockIdx.x;
+// Loads the IPT consecutive elements of this thread plus one neighbour on each side and
+// returns the flag bits f (bit j = flag of element l0 + j, j = 0..IPT; beyond-the-end counts
+// as flagged).  kx[j+1] / sx[j+1] belong to element l0 + j.
+template <int IPT, bool ROUND0>
+__device__ __forceinline__ u32 load_and_flag(const RebuildArgs &a, u32 l0, u64 (&kx)[IPT + 2], u32 (&sx)[IPT + 2]) {
   const u32 L = a.L;
-  const u32 l0 = tile * (u32)TILE + (u32)tid * IPT;
-
-  // ---- load this thread's IPT consecutive elements (+ one neighbour on each side) -------
-  u64 kx[IPT + 2];  // kx[j+1] = key of element l0+j
-  u32 sx[IPT + 2];
-  u32 px[IPT];
   if (l0 + IPT <= L) {
     static_assert(IPT % 4 == 0, "vector loads");
 #pragma unroll
@@ -201,25 +274,13 @@ __global__ void __launch_bounds__(THREADS) k_rebuild(const RebuildArgs a) {
       const uint4 v = *reinterpret_cast<const uint4 *>(a.sufx + l0 + j);
       sx[j + 1] = v.x; sx[j + 2] = v.y; sx[j + 3] = v.z; sx[j + 4] = v.w;
     }
-    if (!ROUND0) {
-#pragma unroll
-      for (int j = 0; j < IPT; j += 4) {
-        const uint4 v = *reinterpret_cast<const uint4 *>(a.pos_in + l0 + j);
-        px[j] = v.x; px[j + 1] = v.y; px[j + 2] = v.z; px[j + 3] = v.w;
-      }
-    }
   } else {
 #pragma unroll
     for (int j = 0; j < IPT; ++j) {
       const bool ok = l0 + j < L;
       kx[j + 1] = ok ? a.keys[l0 + j] : 0;
       sx[j + 1] = ok ? a.sufx[l0 + j] : 0;
-      if (!ROUND0) px[j] = ok ? a.pos_in[l0 + j] : 0;
     }
-  }
-  if (ROUND0) {
-#pragma unroll
-    for (int j = 0; j < IPT; ++j) px[j] = l0 + j;
   }
   const bool has_prev = (l0 > 0) && (l0 <= L);
   const bool has_next = (l0 + IPT < L);
@@ -227,8 +288,6 @@ __global__ void __launch_bounds__(THREADS) k_rebuild(const RebuildArgs a) {
   sx[0] = has_prev ? a.sufx[l0 - 1] : 0;
   kx[IPT + 1] = has_next ? a.keys[l0 + IPT] : 0;
   sx[IPT + 1] = has_next ? a.sufx[l0 + IPT] : 0;
-
-  // ---- flags f[j] for elements l0+j, j = 0..IPT (bit j); beyond-the-end counts as flagged ----
   u32 f = 0;
 #pragma unroll
   for (int j = 0; j <= IPT; ++j) {
@@ -237,11 +296,107 @@ __global__ void __launch_bounds__(THREADS) k_rebuild(const RebuildArgs a) {
     if (ROUND0) fl = fl || (sx[j + 1] >= a.short_from) || (sx[j] >= a.short_from);
     f |= (fl ? 1u : 0u) << j;
   }
+  return f;
+}
+
+template <int THREADS, int IPT, bool ROUND0>
+__global__ void __launch_bounds__(THREADS) k_tail_summary(const RebuildArgs a) {
+  constexpr int WARPS = THREADS / 32;
+  __shared__ u32 s_w[WARPS];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const u32 tile = blockIdx.x;
+  const u32 l0 = tile * (u32)(THREADS * IPT) + (u32)tid * IPT;
+  u64 kx[IPT + 2];
+  u32 sx[IPT + 2];
+  const u32 f = load_and_flag<IPT, ROUND0>(a, l0, kx, sx);
+  u32 v = NO_TAIL;
+  if (l0 < a.L) {
+    const u32 nvalid = min((u32)IPT, a.L - l0);
+    const u32 tails = (f >> 1) & ((1u << nvalid) - 1u);  // element j is a tail iff element j+1 is flagged
+    if (tails) {
+      const u32 l = l0 + (u32)(__ffs(tails) - 1);
+      v = ROUND0 ? l : a.pos_in[l];
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+  if (lane == 0) s_w[warp] = v;
+  __syncthreads();
+  if (tid == 0) {
+    u32 m = NO_TAIL;
+#pragma unroll
+    for (int w = 0; w < WARPS; ++w) m = min(m, s_w[w]);
+    a.tile_tail[tile] = m;
+  }
+}
+
+// next_tail[t] = min over tiles t' > t of tile_tail[t'] (slots ascend, so the minimum is the nearest).
+__global__ void __launch_bounds__(1024) k_tail_scan(const u32 *__restrict__ tile_tail, u32 *__restrict__ next_tail, u32 tiles) {
+  __shared__ u32 s_v[1024];
+  const u32 t = threadIdx.x;
+  const u32 per = (tiles + 1023u) / 1024u;
+  const u32 lo = min(tiles, t * per), hi = min(tiles, lo + per);
+  u32 m = NO_TAIL;
+  for (u32 i = lo; i < hi; ++i) m = min(m, tile_tail[i]);
+  s_v[t] = m;
+  __syncthreads();
+  // exclusive suffix-min over the 1024 chunk minima (Hillis-Steele on a copy shifted by one)
+  u32 x = (t + 1 < 1024) ? s_v[t + 1] : NO_TAIL;
+  __syncthreads();
+  s_v[t] = x;
+  __syncthreads();
+  for (u32 o = 1; o < 1024; o <<= 1) {
+    const u32 y = (t + o < 1024) ? s_v[t + o] : NO_TAIL;
+    __syncthreads();
+    s_v[t] = min(s_v[t], y);
+    __syncthreads();
+  }
+  u32 carry = s_v[t];  // min over all chunks to the right of mine
+  for (u32 i = hi; i > lo; --i) {
+    next_tail[i - 1] = carry;
+    carry = min(carry, tile_tail[i - 1]);
+  }
+}
+
+template <int THREADS, int IPT, bool ROUND0>
+__global__ void __launch_bounds__(THREADS) k_rebuild(const RebuildArgs a) {
+  constexpr int WARPS = THREADS / 32;
+  constexpr int TILE = THREADS * IPT;
+  __shared__ u32 s_wh[WARPS], s_wc[WARPS], s_wg[WARPS], s_wt[WARPS];
+  __shared__ u32 s_pre[3];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // Tiles are taken in blockIdx order: the look-back only ever waits on lower-numbered
+  // blocks, which the hardware dispatches first.
+  const u32 tile = blockIdx.x;
+  const u32 L = a.L;
+  const u32 l0 = tile * (u32)TILE + (u32)tid * IPT;
+
+  u64 kx[IPT + 2];
+  u32 sx[IPT + 2];
+  u32 px[IPT];
+  const u32 f = load_and_flag<IPT, ROUND0>(a, l0, kx, sx);
+  if (ROUND0) {
+#pragma unroll
+    for (int j = 0; j < IPT; ++j) px[j] = l0 + j;
+  } else if (l0 + IPT <= L) {
+#pragma unroll
+    for (int j = 0; j < IPT; j += 4) {
+      const uint4 v = *reinterpret_cast<const uint4 *>(a.pos_in + l0 + j);
+      px[j] = v.x; px[j + 1] = v.y; px[j + 2] = v.z; px[j + 3] = v.w;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < IPT; ++j) px[j] = (l0 + j < L) ? a.pos_in[l0 + j] : 0;
+  }
   u32 nvalid = 0;
   if (l0 < L) nvalid = min((u32)IPT, L - l0);
 
   // ---- thread aggregates ------------------------------------------------------------------
   u32 th = 0, tc = 0, tg = 0;  // last flagged slot + 1, survivors, surviving group heads
+  u32 tt = NO_TAIL;            // first tail slot
+#pragma unroll
+  for (int j = IPT - 1; j >= 0; --j)
+    if ((u32)j < nvalid && ((f >> (j + 1)) & 1u)) tt = px[j];
 #pragma unroll
   for (int j = 0; j < IPT; ++j) {
     if ((u32)j < nvalid) {
@@ -251,19 +406,23 @@ __global__ void __launch_bounds__(THREADS) k_rebuild(const RebuildArgs a) {
       if (fj && !fn) ++tg;
     }
   }
-  // ---- block exclusive scan of (max, sum, sum) -------------------------------------------------
-  u32 ih = th, ic = tc, ig = tg;
+  // ---- block scans: forward (max, sum, sum) and backward (min) ---------------------------------
+  u32 ih = th, ic = tc, ig = tg, it = tt;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
     const u32 yh = __shfl_up_sync(0xffffffffu, ih, o);
     const u32 yc = __shfl_up_sync(0xffffffffu, ic, o);
     const u32 yg = __shfl_up_sync(0xffffffffu, ig, o);
+    const u32 yt = __shfl_down_sync(0xffffffffu, it, o);
     if (lane >= o) { ih = max(ih, yh); ic += yc; ig += yg; }
+    if (lane + o < 32) it = min(it, yt);
   }
   if (lane == 31) { s_wh[warp] = ih; s_wc[warp] = ic; s_wg[warp] = ig; }
-  // exclusive within warp
+  if (lane == 0) s_wt[warp] = it;
   u32 eh = __shfl_up_sync(0xffffffffu, ih, 1), ec = ic - tc, eg = ig - tg;
+  u32 et = __shfl_down_sync(0xffffffffu, it, 1);
   if (lane == 0) eh = 0;
+  if (lane == 31) et = NO_TAIL;
   __syncthreads();
   u32 bh = 0, bc = 0, bg = 0;  // block totals (all warps)
   {
@@ -272,9 +431,11 @@ __global__ void __launch_bounds__(THREADS) k_rebuild(const RebuildArgs a) {
     for (int w = 0; w < WARPS; ++w) {
       if (w == warp) { ph = bh; pc = bc; pg = bg; }
       bh = max(bh, s_wh[w]); bc += s_wc[w]; bg += s_wg[w];
+      if (w > warp) et = min(et, s_wt[w]);
     }
     eh = max(eh, ph); ec += pc; eg += pg;
   }
+  et = min(et, a.next_tail[tile]);  // first tail slot after this thread's elements
 
   // ---- tile prefix by decoupled look-back (warp 0, 32 predecessors per round trip) ----------
   if (warp == 0) {
@@ -320,23 +481,29 @@ __global__ void __launch_bounds__(THREADS) k_rebuild(const RebuildArgs a) {
   __syncthreads();
 
   // ---- emit ------------------------------------------------------------------------------------
+  u32 tl[IPT];  // tail slot of every element
+  {
+    u32 cur = et;
+#pragma unroll
+    for (int j = IPT - 1; j >= 0; --j) {
+      if ((u32)j < nvalid && ((f >> (j + 1)) & 1u)) cur = px[j];
+      tl[j] = cur;
+    }
+  }
   u32 head = max(s_pre[0], eh);  // head slot + 1
   u32 c = s_pre[1] + ec;
-  u32 g = s_pre[2] + eg;
 #pragma unroll
   for (int j = 0; j < IPT; ++j) {
     if ((u32)j < nvalid) {
-      const bool fj = (f >> j) & 1u, fn = (f >> (j + 1)) & 1u;
-      if (fj) head = px[j] + 1u;
-      a.rank[sx[j + 1]] = head;
-      if (fj && fn) {
+      if ((f >> j) & 1u) head = px[j] + 1u;
+      const u32 s1 = head, e1 = tl[j] + 1u;  // label range of the group: [s1, e1]
+      if (s1 == e1) {
         a.SA[px[j]] = (i32)sx[j + 1];
+        a.rank[sx[j + 1]] = RANK_DEAD | s1;
       } else {
-        if (fj) ++g;
-        a.pos_out[c] = px[j];
-        a.sufx_out[c] = sx[j + 1];
-        a.ord_out[c] = g - 1u;
-        ++c;
+        const u32 old = ROUND0 ? 0u : (u32)(kx[j + 1] >> a.lab_bits);
+        if (old < s1 || old > e1) a.rank[sx[j + 1]] = s1 + ((e1 - s1) >> 1);
+        a.pos_out[c++] = px[j];
       }
     }
   }
@@ -354,6 +521,8 @@ constexpr int RB_THREADS = 512;
 constexpr int RB_IPT = 8;
 constexpr int RB_TILE = RB_THREADS * RB_IPT;
 constexpr int HIST_THREADS = 512;
+constexpr int GA_THREADS = 512;
+constexpr int GA_IPT = 8;
 
 struct Carve {
   char *p;
@@ -368,14 +537,16 @@ struct Carve {
 
 struct Layout {
   u64 *packed; u64 packed_words;
-  u64 *keys[2]; u32 *vals[2]; u32 *pos[2]; u32 *ord; u32 *rank;
+  u64 *keys[2]; u32 *vals[2]; u32 *pos[2]; u32 *lst[2]; u32 *rank;
   u32 *ghist;      // [MAX_PASSES][256]
   u32 *bin_base;   // [MAX_PASSES][256]
   u32 *present;    // [256]
   u32 *skip_mask;  // [1]
+  u32 *live_counter;  // [1]
   RoundResult *result;
   u32 *pass_status; size_t pass_status_words;  // counter at word 0 (256-word header), then [tiles][256]
-  ulonglong2 *rb_status; size_t rb_status_words;  // one 16-byte descriptor per rebuild tile
+  ulonglong2 *rb_status;                       // one 16-byte descriptor per rebuild tile
+  u32 *tile_tail, *next_tail;                  // per rebuild tile
   size_t total;
 };
 
@@ -388,19 +559,21 @@ Layout make_layout(char *base, u32 n) {
   y.keys[0] = c.take<u64>(N); y.keys[1] = c.take<u64>(N);
   y.vals[0] = c.take<u32>(N); y.vals[1] = c.take<u32>(N);
   y.pos[0] = c.take<u32>(N);  y.pos[1] = c.take<u32>(N);
-  y.ord = c.take<u32>(N);
+  y.lst[0] = c.take<u32>(N);  y.lst[1] = c.take<u32>(N);
   y.rank = c.take<u32>(N);
   y.ghist = c.take<u32>(MAX_PASSES * RADIX);
   y.bin_base = c.take<u32>(MAX_PASSES * RADIX);
   y.present = c.take<u32>(256);
   y.skip_mask = c.take<u32>(64);
+  y.live_counter = c.take<u32>(64);
   y.result = c.take<RoundResult>(16);
   const size_t ptiles = div_up(N, PASS_TILE);
   y.pass_status_words = 256 + ptiles * RADIX;
   y.pass_status = c.take<u32>(y.pass_status_words);
   const size_t rtiles = div_up(N, RB_TILE);
-  y.rb_status_words = rtiles + 1;
-  y.rb_status = c.take<ulonglong2>(y.rb_status_words);
+  y.rb_status = c.take<ulonglong2>(rtiles + 1);
+  y.tile_tail = c.take<u32>(rtiles + 1);
+  y.next_tail = c.take<u32>(rtiles + 1);
   y.total = c.used;
   return y;
 }
@@ -440,8 +613,8 @@ struct PassTimer {
 
 // Runs the radix passes for digits [0, npass) on `L` elements whose histograms are already
 // in y.ghist.  `cur` is the buffer index holding the input (ignored when gen != null: the
-// first pass then generates the keys and writes buffer 0).  Returns the index of the buffer
-// holding the sorted pairs.
+// first pass then generates the keys and writes buffer 0).  *cur_out = buffer holding the
+// sorted pairs.
 static int run_passes(const Layout &y, u32 L, int npass, int cur, const KeyGen *gen, cudaStream_t st,
                       gsa_build_stats *stats, PassTimer &timer, int *cur_out, u32 *passes_done) {
   GSA_TRY(cudaMemsetAsync(y.skip_mask, 0, sizeof(u32), st));
@@ -531,22 +704,6 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
     GSA_TRY(cudaGetDevice(&dev));
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   }
-  // The rank gather / scatter of the doubling rounds touches 4 bytes per 32-byte sector at
-  // random; ask L2 not to widen those misses to 64/128-byte DRAM fetches (ncu: 126 B of DRAM
-  // read per gathered rank at the default setting).  Restored before returning.
-  struct L2Fetch {
-    size_t old = 0;
-    bool changed = false;
-    L2Fetch() {
-      const char *e = getenv("GSA_L2_FETCH");
-      const size_t want = e ? (size_t)atoi(e) : 32;
-      if (want == 0) return;  // GSA_L2_FETCH=0: leave the device setting alone
-      if (cudaDeviceGetLimit(&old, cudaLimitMaxL2FetchGranularity) != cudaSuccess) { cudaGetLastError(); return; }
-      if (old != want && cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, want) == cudaSuccess) changed = true;
-      else cudaGetLastError();
-    }
-    ~L2Fetch() { if (changed) { cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, old); cudaGetLastError(); } }
-  } l2fetch_guard;
   cudaEvent_t ev[4];
   for (auto &e : ev) GSA_TRY(cudaEventCreate(&e));
   struct EvFree { cudaEvent_t *e; ~EvFree() { for (int i = 0; i < 4; ++i) cudaEventDestroy(e[i]); } } ev_guard{ev};
@@ -602,6 +759,7 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
   GSA_TRY_RC(run_passes(y, n, npass0, 0, &gen, st, stats, timer, &cur, &passes));
   GSA_TRY(cudaEventRecord(ev[2], st));
 
+  const u32 lab_bits = bits_for(n);  // labels are 1..n
   auto launch_rebuild = [&](bool round0, u32 L, int kv, int pin, int pout) -> int {
     const u32 tiles = (u32)div_up(L, RB_TILE);
     GSA_TRY(cudaMemsetAsync(y.rb_status, 0, (size_t)tiles * sizeof(ulonglong2), st));
@@ -610,16 +768,27 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
     r.pos_in = round0 ? nullptr : y.pos[pin];
     r.L = L;
     r.short_from = round0 ? (n - ns) : 0xffffffffu;
+    r.lab_bits = lab_bits;
     r.rank = y.rank; r.SA = d_SA;
-    r.pos_out = y.pos[pout]; r.sufx_out = y.vals[kv ^ 1]; r.ord_out = y.ord;
+    r.pos_out = y.pos[pout];
     r.status = y.rb_status;
+    r.tile_tail = y.tile_tail; r.next_tail = y.next_tail;
     r.result = y.result;
-    if (round0)
+    if (round0) {
+      k_tail_summary<RB_THREADS, RB_IPT, true><<<tiles, RB_THREADS, 0, st>>>(r);
+      KLAUNCH_CHECK();
+      k_tail_scan<<<1, 1024, 0, st>>>(y.tile_tail, y.next_tail, tiles);
+      KLAUNCH_CHECK();
       k_rebuild<RB_THREADS, RB_IPT, true><<<tiles, RB_THREADS, 0, st>>>(r);
-    else
+    } else {
+      k_tail_summary<RB_THREADS, RB_IPT, false><<<tiles, RB_THREADS, 0, st>>>(r);
+      KLAUNCH_CHECK();
+      k_tail_scan<<<1, 1024, 0, st>>>(y.tile_tail, y.next_tail, tiles);
+      KLAUNCH_CHECK();
       k_rebuild<RB_THREADS, RB_IPT, false><<<tiles, RB_THREADS, 0, st>>>(r);
+    }
     KLAUNCH_CHECK();
-    if (stats) stats->kernel_launches++;
+    if (stats) stats->kernel_launches += 3;
     return GSA_OK;
   };
 
@@ -630,35 +799,43 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
   GSA_TRY(cudaStreamSynchronize(st));
   u32 round = 0;
   auto log_round = [&](u64 depth, u64 live, u32 groups, u32 kb, u32 np) {
-    if (!stats || round >= GSA_MAX_ROUNDS) return;
+    const float pass_ms = timer.drain();
+    if (!stats) return;
+    stats->ms_radix_passes += pass_ms;
+    if (round >= GSA_MAX_ROUNDS) return;
     gsa_round_stat &s = stats->round[round];
     s.depth = depth; s.live = live; s.groups = groups; s.key_bits = kb; s.passes = np;
     cudaEventElapsedTime(&s.ms_total, ev[0], ev[3]);
     cudaEventElapsedTime(&s.ms_sort, ev[1], ev[2]);
-    stats->ms_radix_passes += timer.drain();
     stats->rounds = round + 1;
   };
   log_round(k, n, 0, key_bits, passes);
 
   // ---- doubling rounds ------------------------------------------------------------------------
-  int vcur = cur ^ 1;  // buffer holding the live suffixes
-  int pcur = 0;        // pos buffer holding their slots
+  int pcur = 0;        // pos buffer holding the slots of the live elements (SA order)
+  int lcur = 0;        // lst buffer holding the candidates (text order); round 1 uses 0..n-1
+  u32 Lcand = n;
+  bool ident = true;
   u64 h = k;           // suffixes are sorted by their first h symbols
-  const u32 rank_bits = bits_for(n);  // ranks are 0..n
+  const u32 kb = 2 * lab_bits;
+  const int npass = (int)div_up(kb, 8);
   while (rr.live_out > 0) {
     ++round;
     const u32 L = rr.live_out, G = rr.groups_out;
-    const u32 kb = bits_for(G > 0 ? G - 1 : 0) + rank_bits;
-    const int npass = (int)div_up(kb, 8);
     GSA_TRY(cudaEventRecord(ev[0], st));
     GSA_TRY(cudaMemsetAsync(y.ghist, 0, MAX_PASSES * RADIX * sizeof(u32), st));
-    const u32 gblocks = (u32)std::min<u64>((u64)sms * 4, std::max<u64>(1, div_up(L, HIST_THREADS)));
-    k_gather_hist<HIST_THREADS><<<gblocks, HIST_THREADS, 0, st>>>(y.vals[vcur], y.ord, y.rank, y.keys[vcur], L, n, h,
-                                                                 rank_bits, npass, y.ghist);
+    GSA_TRY(cudaMemsetAsync(y.live_counter, 0, sizeof(u32), st));
+    GatherArgs g;
+    g.lst_in = ident ? nullptr : y.lst[lcur];
+    g.Lin = Lcand; g.rank = y.rank; g.n = n; g.h = h; g.lab_bits = lab_bits; g.npass = npass;
+    g.keys_out = y.keys[0]; g.vals_out = y.vals[0]; g.lst_out = y.lst[lcur ^ 1];
+    g.counter = y.live_counter; g.ghist = y.ghist;
+    const u32 gblocks = (u32)std::min<u64>((u64)sms * 3, std::max<u64>(1, div_up(Lcand, GA_THREADS * GA_IPT)));
+    k_gather<GA_THREADS, GA_IPT><<<gblocks, GA_THREADS, 0, st>>>(g);
     KLAUNCH_CHECK();
     if (stats) stats->kernel_launches++;
     GSA_TRY(cudaEventRecord(ev[1], st));
-    GSA_TRY_RC(run_passes(y, L, npass, vcur, nullptr, st, stats, timer, &cur, &passes));
+    GSA_TRY_RC(run_passes(y, L, npass, 0, nullptr, st, stats, timer, &cur, &passes));
     GSA_TRY(cudaEventRecord(ev[2], st));
     GSA_TRY_RC(launch_rebuild(false, L, cur, pcur, pcur ^ 1));
     GSA_TRY(cudaMemcpyAsync(&rr, y.result, sizeof(rr), cudaMemcpyDeviceToHost, st));
@@ -666,8 +843,10 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
     GSA_TRY(cudaStreamSynchronize(st));
     h *= 2;
     log_round(h, L, G, kb, passes);
-    vcur = cur ^ 1;
     pcur ^= 1;
+    lcur ^= 1;
+    Lcand = L;
+    ident = false;
     if (round > 64) { set_error("prefix doubling did not converge", __FILE__, __LINE__); return GSA_ECUDA; }
   }
   GSA_TRY(cudaEventRecord(ev_all1, st));

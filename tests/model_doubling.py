@@ -1,14 +1,23 @@
-"""numpy model of the GPU construction scheme (TEST INFRASTRUCTURE).
+"""numpy/python model of the GPU construction scheme (TEST INFRASTRUCTURE).
 
-Mirrors stringsearch_b200/csrc/sa_build.cu step by step on the CPU -- alphabet
-compaction, bit-packed round-0 keys with the short-suffix ordering, (group ordinal,
-rank[i+h]) keys, flag/scan rank rebuild, singleton finalisation, live-set compaction --
-so the *design* can be checked against the oracle without a GPU.  It is not used by the
-product and is far too slow for real inputs.
+Mirrors stringsearch_b200/csrc/sa_build.cu step by step on the CPU so the *design* can be
+checked against the oracle without a GPU:
+
+* alphabet compaction, bit-packed round-0 keys, short-suffix ordering;
+* rank[i] = "label" of i's group: any SA slot inside the group's slot range, +1 (0 = past the
+  end).  A group keeps its label across rounds while the label stays inside its (shrinking)
+  range, so most suffixes of a big group never need their rank rewritten; a new label is the
+  middle of the new range;
+* live suffixes are walked in (any) text-order list, key = (label(i) << 31) | label(i + h);
+* sort, flag, head/tail scans, singleton finalisation (dead bit), slot compaction.
+
+Not used by the product; far too slow for real inputs.
 """
 from __future__ import annotations
 
 import numpy as np
+
+DEAD = 1 << 31
 
 
 def bits_for(v: int) -> int:
@@ -18,21 +27,19 @@ def bits_for(v: int) -> int:
     return b
 
 
-def build_sa_model(text: bytes, log=None) -> np.ndarray:
+def build_sa_model(text: bytes, log=None, shuffle_seed=None) -> np.ndarray:
     t = np.frombuffer(bytes(text), dtype=np.uint8)
     n = t.size
     if n == 0:
         return np.zeros(0, np.int32)
     present = np.zeros(256, bool)
     present[t] = True
-    code = np.cumsum(present) - present  # exclusive count of present bytes below c
+    code = np.cumsum(present) - present
     sigma = int(present.sum())
     b = bits_for(sigma - 1 if sigma > 1 else 1)
     k = 64 // b
-    key_bits = k * b
     ns = min(k - 1, n)
     codes = code[t].astype(object)
-    # key(i) = next k symbols, zero padded (python ints: exact 64-bit arithmetic)
     keys = []
     for i in range(n):
         x = 0
@@ -40,57 +47,72 @@ def build_sa_model(text: bytes, log=None) -> np.ndarray:
             x = (x << b) | (int(codes[i + s]) if i + s < n else 0)
         keys.append(x)
     init = [n - 1 - j if j < ns else j - ns for j in range(n)]
-    order = sorted(range(n), key=lambda j: keys[init[j]])  # python sort is stable
-    sufx = np.array([init[j] for j in order], dtype=np.int64)
+    order = sorted(range(n), key=lambda j: keys[init[j]])  # stable
+    sufx = [init[j] for j in order]
     skey = [keys[i] for i in sufx]
     short_from = n - ns
     SA = np.full(n, -1, np.int64)
-    rank = np.zeros(n, np.int64)
+    rank = [0] * n
+    rng = np.random.default_rng(shuffle_seed) if shuffle_seed is not None else None
 
     def rebuild(skey, sufx, pos, round0):
         L = len(sufx)
-        flag = np.zeros(L + 1, bool)
+        flag = [False] * (L + 1)
         flag[L] = True
         for l in range(L):
             f = l == 0 or skey[l] != skey[l - 1]
             if round0:
                 f = f or sufx[l] >= short_from or (l > 0 and sufx[l - 1] >= short_from)
             flag[l] = f
-        head = 0
-        g = 0
-        out_pos, out_sufx, out_ord = [], [], []
+        head = [0] * L
+        tail = [0] * L
+        cur = 0
         for l in range(L):
             if flag[l]:
-                head = pos[l] + 1
-            rank[sufx[l]] = head
-            if flag[l] and flag[l + 1]:
-                assert SA[pos[l]] == -1
-                SA[pos[l]] = sufx[l]
-            else:
-                if flag[l]:
-                    g += 1
-                out_pos.append(pos[l]); out_sufx.append(sufx[l]); out_ord.append(g - 1)
-        return np.array(out_pos, np.int64), np.array(out_sufx, np.int64), np.array(out_ord, np.int64), g
-
-    pos, sufx, ordv, G = rebuild(skey, sufx, np.arange(n), True)
-    h = k
-    rank_bits = bits_for(n)
-    rounds = 1
-    while len(sufx):
-        L = len(sufx)
-        key = []
+                cur = pos[l]
+            head[l] = cur
+        for l in range(L - 1, -1, -1):
+            if flag[l + 1]:
+                cur = pos[l]
+            tail[l] = cur
+        out_pos = []
+        writes = 0
         for l in range(L):
-            tpos = int(sufx[l]) + h
-            r2 = int(rank[tpos]) if tpos < n else 0
-            key.append((int(ordv[l]) << rank_bits) | r2)
-        kb = bits_for(G - 1 if G > 0 else 0) + rank_bits
-        assert all(x < (1 << kb) for x in key) and kb <= 64
-        order = sorted(range(L), key=lambda l: key[l])
+            s, e = head[l], tail[l]
+            old = 0 if round0 else (skey[l] >> 31)
+            keep = s + 1 <= old <= e + 1
+            if s == e:
+                assert SA[s] == -1
+                SA[s] = sufx[l]
+                rank[sufx[l]] = DEAD | (s + 1)
+                writes += 1
+            else:
+                if not keep:
+                    rank[sufx[l]] = s + (e - s) // 2 + 1
+                    writes += 1
+                out_pos.append(pos[l])
+        return out_pos, writes
+
+    pos, _ = rebuild(skey, sufx, list(range(n)), True)
+    lst = list(range(n))  # candidates (identity list in round 1)
+    h = k
+    rounds = 1
+    while pos:
+        live = [i for i in lst if not (rank[i] & DEAD)]
+        if rng is not None:
+            rng.shuffle(live)  # the order of the sort input is irrelevant
+        assert len(live) == len(pos)
+        key = []
+        for i in live:
+            r2 = (rank[i + h] & (DEAD - 1)) if i + h < n else 0
+            key.append(((rank[i] & (DEAD - 1)) << 31) | r2)
+        order = sorted(range(len(live)), key=lambda l: key[l])
         skey = [key[l] for l in order]
-        sufx = sufx[order]
+        sufx = [live[l] for l in order]
+        pos, writes = rebuild(skey, sufx, pos, False)
         if log is not None:
-            log.append((h, L, G, kb))
-        pos, sufx, ordv, G = rebuild(skey, sufx, pos, False)
+            log.append((h, len(live), writes))
+        lst = live
         h *= 2
         rounds += 1
         assert rounds < 70
