@@ -138,8 +138,8 @@ struct GatherArgs {
   u32 *ghist;
 };
 
-template <int THREADS, int IPT>
-__global__ void __launch_bounds__(THREADS) k_gather(const GatherArgs a) {
+template <int THREADS, int IPT, int MIN_BLOCKS>
+__global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_gather(const GatherArgs a) {
   constexpr int WARPS = THREADS / 32;
   constexpr u32 CH = THREADS * IPT;
   __shared__ u32 shist[MAX_PASSES * RADIX];
@@ -153,29 +153,27 @@ __global__ void __launch_bounds__(THREADS) k_gather(const GatherArgs a) {
   for (u32 chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
     // warp w owns the contiguous sub-chunk [w*32*IPT, (w+1)*32*IPT); row k = 32 consecutive candidates
     const u32 wb = chunk * CH + (u32)warp * (32u * IPT) + (u32)lane;
-    u32 sfx[IPT];
-    u64 key[IPT];
-    u32 off[IPT];  // slot offset inside the warp's output run
-    bool live[IPT];
-    u32 wtot = 0;
+    u32 sfx[IPT], w[IPT], r2[IPT];
+    // three rounds of independent loads: candidates, their ranks, the ranks h further on
 #pragma unroll
     for (int k = 0; k < IPT; ++k) {
       const u32 c = wb + (u32)k * 32u;
-      bool lv = false;
-      u32 i = 0, w = 0;
-      if (c < a.Lin) {
-        i = a.lst_in ? ld_stream_u32(a.lst_in + c) : c;
-        w = __ldg(a.rank + i);
-        lv = (w & RANK_DEAD) == 0u;
-      }
-      u64 kx = 0;
-      if (lv) {
-        const u64 t = (u64)i + a.h;
-        const u32 r2 = (t < a.n) ? (__ldg(a.rank + t) & RANK_MASK) : 0u;
-        kx = ((u64)w << a.lab_bits) | r2;
-      }
+      sfx[k] = (c < a.Lin) ? (a.lst_in ? __ldg(a.lst_in + c) : c) : 0xffffffffu;
+    }
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) w[k] = (sfx[k] != 0xffffffffu) ? __ldg(a.rank + sfx[k]) : RANK_DEAD;
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) {
+      const u64 t = (u64)sfx[k] + a.h;
+      r2[k] = (!(w[k] & RANK_DEAD) && t < a.n) ? (__ldg(a.rank + t) & RANK_MASK) : 0u;
+    }
+    u32 off[IPT];  // slot offset inside the warp's output run
+    u32 wtot = 0;
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) {
+      const bool lv = (w[k] & RANK_DEAD) == 0u;
+      const u64 kx = lv ? (((u64)w[k] << a.lab_bits) | r2[k]) : 0ull;
       const u32 m = __ballot_sync(0xffffffffu, lv);
-      sfx[k] = i; key[k] = kx; live[k] = lv;
       off[k] = wtot + (u32)__popc(m & lt);
       wtot += (u32)__popc(m);
       hist_add(shist, kx, lv, a.npass);
@@ -185,16 +183,16 @@ __global__ void __launch_bounds__(THREADS) k_gather(const GatherArgs a) {
     if (tid == 0) {
       u32 tot = 0;
 #pragma unroll
-      for (int w = 0; w < WARPS; ++w) { const u32 c = s_wcnt[w]; s_wcnt[w] = tot; tot += c; }
+      for (int x = 0; x < WARPS; ++x) { const u32 c = s_wcnt[x]; s_wcnt[x] = tot; tot += c; }
       s_base = tot ? atomicAdd(a.counter, tot) : 0u;
     }
     __syncthreads();
     const u32 base = s_base + s_wcnt[warp];
 #pragma unroll
     for (int k = 0; k < IPT; ++k) {
-      if (live[k]) {
+      if ((w[k] & RANK_DEAD) == 0u) {
         const u32 o = base + off[k];
-        a.keys_out[o] = key[k];
+        a.keys_out[o] = ((u64)w[k] << a.lab_bits) | r2[k];
         a.vals_out[o] = sfx[k];
         a.lst_out[o] = sfx[k];
       }
@@ -359,7 +357,7 @@ __global__ void __launch_bounds__(1024) k_tail_scan(const u32 *__restrict__ tile
 }
 
 template <int THREADS, int IPT, bool ROUND0>
-__global__ void __launch_bounds__(THREADS) k_rebuild(const RebuildArgs a) {
+__global__ void __launch_bounds__(THREADS, 2) k_rebuild(const RebuildArgs a) {
   constexpr int WARPS = THREADS / 32;
   constexpr int TILE = THREADS * IPT;
   __shared__ u32 s_wh[WARPS], s_wc[WARPS], s_wg[WARPS], s_wt[WARPS];
@@ -521,8 +519,9 @@ constexpr int RB_THREADS = 512;
 constexpr int RB_IPT = 8;
 constexpr int RB_TILE = RB_THREADS * RB_IPT;
 constexpr int HIST_THREADS = 512;
-constexpr int GA_THREADS = 512;
+constexpr int GA_THREADS = 256;
 constexpr int GA_IPT = 8;
+constexpr int GA_BLOCKS_PER_SM = 4;
 
 struct Carve {
   char *p;
@@ -830,8 +829,8 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
     g.Lin = Lcand; g.rank = y.rank; g.n = n; g.h = h; g.lab_bits = lab_bits; g.npass = npass;
     g.keys_out = y.keys[0]; g.vals_out = y.vals[0]; g.lst_out = y.lst[lcur ^ 1];
     g.counter = y.live_counter; g.ghist = y.ghist;
-    const u32 gblocks = (u32)std::min<u64>((u64)sms * 3, std::max<u64>(1, div_up(Lcand, GA_THREADS * GA_IPT)));
-    k_gather<GA_THREADS, GA_IPT><<<gblocks, GA_THREADS, 0, st>>>(g);
+    const u32 gblocks = (u32)std::min<u64>((u64)sms * GA_BLOCKS_PER_SM, std::max<u64>(1, div_up(Lcand, GA_THREADS * GA_IPT)));
+    k_gather<GA_THREADS, GA_IPT, GA_BLOCKS_PER_SM><<<gblocks, GA_THREADS, 0, st>>>(g);
     KLAUNCH_CHECK();
     if (stats) stats->kernel_launches++;
     GSA_TRY(cudaEventRecord(ev[1], st));
