@@ -231,6 +231,7 @@ struct RebuildArgs {
   i32 *SA;
   u32 *pos_out;
   ulonglong2 *status;  // [tiles] x = flag(2) | head+1 ; y = flag(2) | survivors(31) | groups(31)
+  u32 *survivors;      // [1] k_tail_summary: number of elements that stay live after this round
   u32 *tile_tail;      // [tiles] k_tail_summary: first tail slot inside the tile (or NO_TAIL)
   const u32 *next_tail;  // [tiles] k_tail_scan: first tail slot in any later tile
   RoundResult *result;
@@ -307,24 +308,31 @@ __global__ void __launch_bounds__(THREADS) k_tail_summary(const RebuildArgs a) {
   u64 kx[IPT + 2];
   u32 sx[IPT + 2];
   const u32 f = load_and_flag<IPT, ROUND0>(a, l0, kx, sx);
-  u32 v = NO_TAIL;
+  u32 v = NO_TAIL, surv = 0;
   if (l0 < a.L) {
     const u32 nvalid = min((u32)IPT, a.L - l0);
-    const u32 tails = (f >> 1) & ((1u << nvalid) - 1u);  // element j is a tail iff element j+1 is flagged
+    const u32 vm = (1u << nvalid) - 1u;
+    const u32 tails = (f >> 1) & vm;  // element j is a tail iff element j+1 is flagged
     if (tails) {
       const u32 l = l0 + (u32)(__ffs(tails) - 1);
       v = ROUND0 ? l : a.pos_in[l];
     }
+    surv = (u32)__popc(~(f & (f >> 1)) & vm);  // not (head and tail) = not unique yet
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
-  if (lane == 0) s_w[warp] = v;
+  for (int o = 16; o > 0; o >>= 1) {
+    v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+    surv += __shfl_xor_sync(0xffffffffu, surv, o);
+  }
+  __shared__ u32 s_s[WARPS];
+  if (lane == 0) { s_w[warp] = v; s_s[warp] = surv; }
   __syncthreads();
   if (tid == 0) {
-    u32 m = NO_TAIL;
+    u32 m = NO_TAIL, t = 0;
 #pragma unroll
-    for (int w = 0; w < WARPS; ++w) m = min(m, s_w[w]);
+    for (int w = 0; w < WARPS; ++w) { m = min(m, s_w[w]); t += s_s[w]; }
     a.tile_tail[tile] = m;
+    if (t) atomicAdd(a.survivors, t);
   }
 }
 
@@ -356,7 +364,9 @@ __global__ void __launch_bounds__(1024) k_tail_scan(const u32 *__restrict__ tile
   }
 }
 
-template <int THREADS, int IPT, bool ROUND0>
+// FINAL: no element survives this round (k_tail_summary counted them), every group is unique:
+// nobody will read a rank again, so only SA is written.
+template <int THREADS, int IPT, bool ROUND0, bool FINAL>
 __global__ void __launch_bounds__(THREADS, 2) k_rebuild(const RebuildArgs a) {
   constexpr int WARPS = THREADS / 32;
   constexpr int TILE = THREADS * IPT;
@@ -497,7 +507,7 @@ __global__ void __launch_bounds__(THREADS, 2) k_rebuild(const RebuildArgs a) {
       const u32 s1 = head, e1 = tl[j] + 1u;  // label range of the group: [s1, e1]
       if (s1 == e1) {
         a.SA[px[j]] = (i32)sx[j + 1];
-        a.rank[sx[j + 1]] = RANK_DEAD | s1;
+        if (!FINAL) a.rank[sx[j + 1]] = RANK_DEAD | s1;
       } else {
         const u32 old = ROUND0 ? 0u : (u32)(kx[j + 1] >> a.lab_bits);
         if (old < s1 || old > e1) a.rank[sx[j + 1]] = s1 + ((e1 - s1) >> 1);
@@ -541,7 +551,8 @@ struct Layout {
   u32 *bin_base;   // [MAX_PASSES][256]
   u32 *present;    // [256]
   u32 *skip_mask;  // [1]
-  u32 *live_counter;  // [1]
+  u32 *live_counter;  // [1] k_gather
+  u32 *survivors;     // [1] k_tail_summary
   RoundResult *result;
   u32 *pass_status; size_t pass_status_words;  // counter at word 0 (256-word header), then [tiles][256]
   ulonglong2 *rb_status;                       // one 16-byte descriptor per rebuild tile
@@ -565,6 +576,7 @@ Layout make_layout(char *base, u32 n) {
   y.present = c.take<u32>(256);
   y.skip_mask = c.take<u32>(64);
   y.live_counter = c.take<u32>(64);
+  y.survivors = c.take<u32>(64);
   y.result = c.take<RoundResult>(16);
   const size_t ptiles = div_up(N, PASS_TILE);
   y.pass_status_words = 256 + ptiles * RADIX;
@@ -730,7 +742,16 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
     if (present[c]) ++sigma;
   }
   const u32 b = bits_for(sigma > 1 ? sigma - 1 : 1);  // codes 0..sigma-1
-  const u32 k = 64 / b;                               // symbols per round-0 key
+  // Symbols per round-0 key.  64 bits hold 64/b symbols, but sorting more than about
+  // log2(n) + 10 bits only orders suffixes that are (for text without long repeats) already
+  // unique: every 8 bits beyond that is a full radix pass over all n suffixes, while the few
+  // groups that are still tied are cheaper to finish in a doubling round over just them.
+  const u32 k_max = 64 / b;
+  const u32 k_want = (bits_for(n) + 10 + b - 1) / b;
+  const char *k_env = getenv("GSA_KEY_SYMBOLS");  // experiments: force the round-0 depth
+  u32 k = k_env ? (u32)atoi(k_env) : k_want;
+  if (k < 1) k = 1;
+  if (k > k_max) k = k_max;
   const u32 key_bits = k * b;
   const u32 ns = (k - 1 < n) ? (k - 1) : n;           // short suffixes
   const u64 nwords = ((u64)n * b + 63) / 64 + 2;
@@ -759,9 +780,12 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
   GSA_TRY(cudaEventRecord(ev[2], st));
 
   const u32 lab_bits = bits_for(n);  // labels are 1..n
-  auto launch_rebuild = [&](bool round0, u32 L, int kv, int pin, int pout) -> int {
+  // tail summaries + survivor count, then the rebuild proper.  *survivors_out is known before the
+  // rebuild is launched, which lets the last round skip its rank writes.
+  auto launch_rebuild = [&](bool round0, u32 L, int kv, int pin, int pout, u32 *survivors_out) -> int {
     const u32 tiles = (u32)div_up(L, RB_TILE);
     GSA_TRY(cudaMemsetAsync(y.rb_status, 0, (size_t)tiles * sizeof(ulonglong2), st));
+    GSA_TRY(cudaMemsetAsync(y.survivors, 0, sizeof(u32), st));
     RebuildArgs r;
     r.keys = y.keys[kv]; r.sufx = y.vals[kv];
     r.pos_in = round0 ? nullptr : y.pos[pin];
@@ -771,28 +795,31 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
     r.rank = y.rank; r.SA = d_SA;
     r.pos_out = y.pos[pout];
     r.status = y.rb_status;
+    r.survivors = y.survivors;
     r.tile_tail = y.tile_tail; r.next_tail = y.next_tail;
     r.result = y.result;
-    if (round0) {
-      k_tail_summary<RB_THREADS, RB_IPT, true><<<tiles, RB_THREADS, 0, st>>>(r);
-      KLAUNCH_CHECK();
-      k_tail_scan<<<1, 1024, 0, st>>>(y.tile_tail, y.next_tail, tiles);
-      KLAUNCH_CHECK();
-      k_rebuild<RB_THREADS, RB_IPT, true><<<tiles, RB_THREADS, 0, st>>>(r);
-    } else {
-      k_tail_summary<RB_THREADS, RB_IPT, false><<<tiles, RB_THREADS, 0, st>>>(r);
-      KLAUNCH_CHECK();
-      k_tail_scan<<<1, 1024, 0, st>>>(y.tile_tail, y.next_tail, tiles);
-      KLAUNCH_CHECK();
-      k_rebuild<RB_THREADS, RB_IPT, false><<<tiles, RB_THREADS, 0, st>>>(r);
-    }
+    if (round0) k_tail_summary<RB_THREADS, RB_IPT, true><<<tiles, RB_THREADS, 0, st>>>(r);
+    else k_tail_summary<RB_THREADS, RB_IPT, false><<<tiles, RB_THREADS, 0, st>>>(r);
+    KLAUNCH_CHECK();
+    k_tail_scan<<<1, 1024, 0, st>>>(y.tile_tail, y.next_tail, tiles);
+    KLAUNCH_CHECK();
+    u32 surv = 0;
+    GSA_TRY(cudaMemcpyAsync(&surv, y.survivors, sizeof(u32), cudaMemcpyDeviceToHost, st));
+    GSA_TRY(cudaStreamSynchronize(st));
+    *survivors_out = surv;
+    const bool fin = surv == 0;
+    if (round0 && fin) k_rebuild<RB_THREADS, RB_IPT, true, true><<<tiles, RB_THREADS, 0, st>>>(r);
+    else if (round0) k_rebuild<RB_THREADS, RB_IPT, true, false><<<tiles, RB_THREADS, 0, st>>>(r);
+    else if (fin) k_rebuild<RB_THREADS, RB_IPT, false, true><<<tiles, RB_THREADS, 0, st>>>(r);
+    else k_rebuild<RB_THREADS, RB_IPT, false, false><<<tiles, RB_THREADS, 0, st>>>(r);
     KLAUNCH_CHECK();
     if (stats) stats->kernel_launches += 3;
     return GSA_OK;
   };
 
   RoundResult rr{};
-  GSA_TRY_RC(launch_rebuild(true, n, cur, 0, 0));
+  u32 survivors = 0;
+  GSA_TRY_RC(launch_rebuild(true, n, cur, 0, 0, &survivors));
   GSA_TRY(cudaMemcpyAsync(&rr, y.result, sizeof(rr), cudaMemcpyDeviceToHost, st));
   GSA_TRY(cudaEventRecord(ev[3], st));
   GSA_TRY(cudaStreamSynchronize(st));
@@ -836,7 +863,7 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
     GSA_TRY(cudaEventRecord(ev[1], st));
     GSA_TRY_RC(run_passes(y, L, npass, 0, nullptr, st, stats, timer, &cur, &passes));
     GSA_TRY(cudaEventRecord(ev[2], st));
-    GSA_TRY_RC(launch_rebuild(false, L, cur, pcur, pcur ^ 1));
+    GSA_TRY_RC(launch_rebuild(false, L, cur, pcur, pcur ^ 1, &survivors));
     GSA_TRY(cudaMemcpyAsync(&rr, y.result, sizeof(rr), cudaMemcpyDeviceToHost, st));
     GSA_TRY(cudaEventRecord(ev[3], st));
     GSA_TRY(cudaStreamSynchronize(st));

@@ -27,7 +27,7 @@ def bits_for(v: int) -> int:
     return b
 
 
-def build_sa_model(text: bytes, log=None, shuffle_seed=None) -> np.ndarray:
+def build_sa_model(text: bytes, log=None, shuffle_seed=None, key_symbols=None) -> np.ndarray:
     t = np.frombuffer(bytes(text), dtype=np.uint8)
     n = t.size
     if n == 0:
@@ -37,7 +37,9 @@ def build_sa_model(text: bytes, log=None, shuffle_seed=None) -> np.ndarray:
     code = np.cumsum(present) - present
     sigma = int(present.sum())
     b = bits_for(sigma - 1 if sigma > 1 else 1)
-    k = 64 // b
+    k = min(64 // b, (bits_for(n) + 10 + b - 1) // b)  # adaptive round-0 depth, as sa_build.cu
+    if key_symbols is not None:
+        k = max(1, min(64 // b, key_symbols))
     ns = min(k - 1, n)
     codes = code[t].astype(object)
     keys = []

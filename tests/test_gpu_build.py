@@ -70,6 +70,20 @@ def test_structured_inputs_match_reference(ref, name, maker):
     print(name, "rounds", stats.rounds, [(r["depth"], r["live"], r["passes"]) for r in stats.rounds_list()])
 
 
+def test_any_round0_depth_gives_the_same_sa(port, monkeypatch):
+    """The round-0 key depth is a tuning knob (GSA_KEY_SYMBOLS); the SA must not depend on it."""
+    from stringsearch_b200 import synth
+
+    texts = [synth.acgt(300_000, 3), synth.random_bytes(200_000, 4), synth.repetitive(400_000, 5, period=77),
+             (synth.random_bytes(100_000, 6) % 3).astype(np.uint8)]
+    for t in texts:
+        exp = port.sa_build(t)
+        for ks in ("1", "2", "3", "7", "64"):
+            monkeypatch.setenv("GSA_KEY_SYMBOLS", ks)
+            _assert_same(_sort(t), exp, f"key_symbols={ks}")
+        monkeypatch.delenv("GSA_KEY_SYMBOLS")
+
+
 def test_tile_boundaries(port):
     """Sizes straddling the radix tile (4096), rebuild tile (2048) and vector widths."""
     rng = np.random.default_rng(7)

@@ -93,8 +93,10 @@ def test_design_model_matches_oracle(port, sa_golden):
     for name, text, sa in sa_golden:
         if len(text) <= 1200:
             assert build_sa_model(text).tolist() == sa.tolist(), name
-    for t in random_cases(seed=21, sizes=(3, 8, 9, 33, 65, 200)):
-        assert (build_sa_model(t) == port.sa_build(t)).all()
+    for i, t in enumerate(random_cases(seed=21, sizes=(3, 8, 9, 33, 65, 200))):
+        assert (build_sa_model(t, shuffle_seed=i) == port.sa_build(t)).all()
+        for ks in (1, 2, 5):  # any round-0 depth must give the same SA
+            assert (build_sa_model(t, key_symbols=ks) == port.sa_build(t)).all()
 
 
 def test_synth_shapes():
