@@ -41,15 +41,20 @@ struct KeyGen {
 };
 
 #ifdef __CUDACC__
-__device__ __forceinline__ void gen_key0(const KeyGen &g, u32 j, u64 &key, u32 &sufx) {
-  const u32 i = (j < g.ns) ? (g.n - 1u - j) : (j - g.ns);
+// Round-0 key of suffix i: its first key_bits / b symbols, zero padded past the text end.
+__device__ __forceinline__ u64 key_of_suffix(const KeyGen &g, u32 i) {
   const u64 bit = (u64)i * g.b;
   const u64 w = bit >> 6;
   const u32 s = (u32)bit & 63u;
   const u64 w0 = __ldg(g.packed + w);
   const u64 w1 = __ldg(g.packed + w + 1);
   const u64 x = s ? ((w0 << s) | (w1 >> (64u - s))) : w0;
-  key = x >> (64u - g.key_bits);
+  return x >> (64u - g.key_bits);
+}
+
+__device__ __forceinline__ void gen_key0(const KeyGen &g, u32 j, u64 &key, u32 &sufx) {
+  const u32 i = (j < g.ns) ? (g.n - 1u - j) : (j - g.ns);
+  key = key_of_suffix(g, i);
   sufx = i;
 }
 

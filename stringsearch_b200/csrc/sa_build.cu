@@ -111,6 +111,29 @@ __global__ void __launch_bounds__(THREADS) k_hist0(const KeyGen g, int npass, u3
 }
 
 // ------------------------------------------------------------------------------------
+// Repetitiveness probe: how many of `m` pseudo-random suffixes share their first
+// key_bits / b symbols with another sampled suffix?  (Open-addressing insert into a small
+// hash table; a hit on an equal key counts as a duplicate.)  Text without long repeats gives
+// ~0; repetitive text gives ~m.  The host uses it to pick the round-0 key depth.
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_sample_dups(const KeyGen g, u32 m, u64 *__restrict__ table, u32 table_mask,
+                                                     u32 *__restrict__ dups) {
+  const u32 s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= m) return;
+  u32 x = s * 2654435761u + 12345u;
+  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+  const u32 i = (u32)(((u64)x * (u64)g.n) >> 32);
+  const u64 key = key_of_suffix(g, i) + 1ull;  // 0 marks an empty table slot
+  u32 slot = (u32)((key * 0x9E3779B97F4A7C15ull) >> 40) & table_mask;
+  for (int probe = 0; probe < 16; ++probe) {
+    const unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long *>(table + slot), 0ull, (unsigned long long)key);
+    if (old == 0ull) return;
+    if (old == key) { atomicAdd(dups, 1u); return; }
+    slot = (slot + 1u) & table_mask;
+  }
+}
+
+// ------------------------------------------------------------------------------------
 // Rounds >= 1, step 1: walk the candidate suffixes in text order, drop the finalised ones,
 // build the sort key of the live ones, histogram its digits, and emit
 //   (key, suffix) -> sort input,   suffix -> next round's candidate list.
@@ -136,7 +159,32 @@ struct GatherArgs {
   u32 *lst_out;
   u32 *counter;  // zeroed before launch; ends at the number of live suffixes
   u32 *ghist;
+  // sparse mode (few suffixes survived round 0): rank[] holds 0 for every suffix that was
+  // already unique after round 0; its label is recomputed on demand from the round-0 order.
+  const i32 *sa0;  // null unless sparse: SA after round 0, every slot filled
+  KeyGen gen;
 };
+
+// Label of a suffix that was unique after round 0 (sparse mode): its SA slot + 1, found by
+// binary search of its round-0 key in the round-0 order.  Equal keys are ordered short
+// suffixes first (shortest first), then the long ones, so a suffix sits behind every short
+// suffix with the same zero-padded key (and, if short itself, only behind the shorter ones).
+__device__ __noinline__ u32 lazy_label(const GatherArgs &a, u32 t) {
+  const KeyGen &g = a.gen;
+  const u64 kt = key_of_suffix(g, t);
+  u32 lo = 0, hi = g.n;
+  while (lo < hi) {
+    const u32 mid = lo + ((hi - lo) >> 1);
+    if (key_of_suffix(g, (u32)__ldg(a.sa0 + mid)) < kt) lo = mid + 1; else hi = mid;
+  }
+  u32 extra = 0;
+  if ((kt & ((1ull << g.b) - 1ull)) == 0ull) {  // only a key ending in symbol 0 can equal a padded one
+    const u32 first_short = g.n - g.ns;
+    const u32 from = (t >= first_short) ? t + 1u : first_short;
+    for (u32 j = from; j < g.n; ++j) extra += (key_of_suffix(g, j) == kt) ? 1u : 0u;
+  }
+  return lo + extra + 1u;
+}
 
 template <int THREADS, int IPT, int MIN_BLOCKS>
 __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_gather(const GatherArgs a) {
@@ -161,11 +209,21 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_gather(const GatherArgs
       sfx[k] = (c < a.Lin) ? (a.lst_in ? __ldg(a.lst_in + c) : c) : 0xffffffffu;
     }
 #pragma unroll
-    for (int k = 0; k < IPT; ++k) w[k] = (sfx[k] != 0xffffffffu) ? __ldg(a.rank + sfx[k]) : RANK_DEAD;
+    for (int k = 0; k < IPT; ++k) {
+      w[k] = (sfx[k] != 0xffffffffu) ? __ldg(a.rank + sfx[k]) : RANK_DEAD;
+      if (w[k] == 0u) w[k] = RANK_DEAD;  // sparse mode: unique since round 0
+    }
 #pragma unroll
     for (int k = 0; k < IPT; ++k) {
       const u64 t = (u64)sfx[k] + a.h;
       r2[k] = (!(w[k] & RANK_DEAD) && t < a.n) ? (__ldg(a.rank + t) & RANK_MASK) : 0u;
+    }
+    if (a.sa0 != nullptr) {
+#pragma unroll 1
+      for (int k = 0; k < IPT; ++k) {
+        const u64 t = (u64)sfx[k] + a.h;
+        if (!(w[k] & RANK_DEAD) && t < a.n && r2[k] == 0u) r2[k] = lazy_label(a, (u32)t);
+      }
     }
     u32 off[IPT];  // slot offset inside the warp's output run
     u32 wtot = 0;
@@ -364,9 +422,14 @@ __global__ void __launch_bounds__(1024) k_tail_scan(const u32 *__restrict__ tile
   }
 }
 
-// FINAL: no element survives this round (k_tail_summary counted them), every group is unique:
-// nobody will read a rank again, so only SA is written.
-template <int THREADS, int IPT, bool ROUND0, bool FINAL>
+// MODE (the survivor count of the round is known from k_tail_summary before the launch):
+//   RB_NORMAL  as described above
+//   RB_FINAL   nothing survives: nobody will read a rank again, only SA is written
+//   RB_SPARSE  round 0 with few survivors: SA gets every element (a complete round-0 order),
+//              rank[] (pre-zeroed) only the labels of the survivors; labels of the unique
+//              suffixes are recomputed on demand (lazy_label) instead of being scattered
+enum { RB_NORMAL = 0, RB_FINAL = 1, RB_SPARSE = 2 };
+template <int THREADS, int IPT, bool ROUND0, int MODE>
 __global__ void __launch_bounds__(THREADS, 2) k_rebuild(const RebuildArgs a) {
   constexpr int WARPS = THREADS / 32;
   constexpr int TILE = THREADS * IPT;
@@ -507,10 +570,11 @@ __global__ void __launch_bounds__(THREADS, 2) k_rebuild(const RebuildArgs a) {
       const u32 s1 = head, e1 = tl[j] + 1u;  // label range of the group: [s1, e1]
       if (s1 == e1) {
         a.SA[px[j]] = (i32)sx[j + 1];
-        if (!FINAL) a.rank[sx[j + 1]] = RANK_DEAD | s1;
+        if (MODE == RB_NORMAL) a.rank[sx[j + 1]] = RANK_DEAD | s1;
       } else {
         const u32 old = ROUND0 ? 0u : (u32)(kx[j + 1] >> a.lab_bits);
         if (old < s1 || old > e1) a.rank[sx[j + 1]] = s1 + ((e1 - s1) >> 1);
+        if (MODE == RB_SPARSE) a.SA[px[j]] = (i32)sx[j + 1];
         a.pos_out[c++] = px[j];
       }
     }
@@ -747,18 +811,35 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
   // unique: every 8 bits beyond that is a full radix pass over all n suffixes, while the few
   // groups that are still tied are cheaper to finish in a doubling round over just them.
   const u32 k_max = 64 / b;
-  const u32 k_want = (bits_for(n) + 10 + b - 1) / b;
-  const char *k_env = getenv("GSA_KEY_SYMBOLS");  // experiments: force the round-0 depth
-  u32 k = k_env ? (u32)atoi(k_env) : k_want;
-  if (k < 1) k = 1;
-  if (k > k_max) k = k_max;
-  const u32 key_bits = k * b;
-  const u32 ns = (k - 1 < n) ? (k - 1) : n;           // short suffixes
+  const u32 k_want = std::min<u32>(k_max, (bits_for(n) + 10 + b - 1) / b);
   const u64 nwords = ((u64)n * b + 63) / 64 + 2;
   {
     k_pack<<<(u32)div_up(nwords, 256), 256, 0, st>>>(d_T, n, b, cm, y.packed, nwords);
     KLAUNCH_CHECK();
   }
+  u32 k = k_want;
+  if (const char *k_env = getenv("GSA_KEY_SYMBOLS")) {  // experiments: force the round-0 depth
+    k = (u32)atoi(k_env);
+  } else if (k_want < k_max && n >= (1u << 22)) {
+    // ... unless the text is repetitive: then nearly everything survives round 0 whatever its
+    // depth, and a deeper start means fewer doubling rounds.
+    constexpr u32 M = 1u << 16, TBL = 1u << 18;
+    u64 *table = reinterpret_cast<u64 *>(y.pos[0]);
+    GSA_TRY(cudaMemsetAsync(table, 0, TBL * sizeof(u64), st));
+    GSA_TRY(cudaMemsetAsync(y.survivors, 0, sizeof(u32), st));
+    KeyGen probe{y.packed, n, 0, b, k_want * b};
+    k_sample_dups<<<M / 256, 256, 0, st>>>(probe, M, table, TBL - 1, y.survivors);
+    KLAUNCH_CHECK();
+    u32 dups = 0;
+    GSA_TRY(cudaMemcpyAsync(&dups, y.survivors, sizeof(u32), cudaMemcpyDeviceToHost, st));
+    GSA_TRY(cudaStreamSynchronize(st));
+    if (dups > M / 8) k = k_max;
+    if (stats) stats->kernel_launches++;
+  }
+  if (k < 1) k = 1;
+  if (k > k_max) k = k_max;
+  const u32 key_bits = k * b;
+  const u32 ns = (k - 1 < n) ? (k - 1) : n;           // short suffixes
   if (stats) {
     stats->sigma = sigma; stats->bits_per_symbol = b; stats->symbols_per_key = k;
     stats->kernel_launches += 2;
@@ -780,6 +861,7 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
   GSA_TRY(cudaEventRecord(ev[2], st));
 
   const u32 lab_bits = bits_for(n);  // labels are 1..n
+  bool sparse = false;
   // tail summaries + survivor count, then the rebuild proper.  *survivors_out is known before the
   // rebuild is launched, which lets the last round skip its rank writes.
   auto launch_rebuild = [&](bool round0, u32 L, int kv, int pin, int pout, u32 *survivors_out) -> int {
@@ -807,11 +889,17 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
     GSA_TRY(cudaMemcpyAsync(&surv, y.survivors, sizeof(u32), cudaMemcpyDeviceToHost, st));
     GSA_TRY(cudaStreamSynchronize(st));
     *survivors_out = surv;
-    const bool fin = surv == 0;
-    if (round0 && fin) k_rebuild<RB_THREADS, RB_IPT, true, true><<<tiles, RB_THREADS, 0, st>>>(r);
-    else if (round0) k_rebuild<RB_THREADS, RB_IPT, true, false><<<tiles, RB_THREADS, 0, st>>>(r);
-    else if (fin) k_rebuild<RB_THREADS, RB_IPT, false, true><<<tiles, RB_THREADS, 0, st>>>(r);
-    else k_rebuild<RB_THREADS, RB_IPT, false, false><<<tiles, RB_THREADS, 0, st>>>(r);
+    if (round0) {
+      // few survivors: do not scatter n ranks for the sake of a handful of look-ups
+      sparse = surv != 0 && (u64)surv * 64 < n && !getenv("GSA_NO_SPARSE");
+      if (sparse) GSA_TRY(cudaMemsetAsync(y.rank, 0, (size_t)n * sizeof(u32), st));
+      if (surv == 0) k_rebuild<RB_THREADS, RB_IPT, true, RB_FINAL><<<tiles, RB_THREADS, 0, st>>>(r);
+      else if (sparse) k_rebuild<RB_THREADS, RB_IPT, true, RB_SPARSE><<<tiles, RB_THREADS, 0, st>>>(r);
+      else k_rebuild<RB_THREADS, RB_IPT, true, RB_NORMAL><<<tiles, RB_THREADS, 0, st>>>(r);
+    } else {
+      if (surv == 0) k_rebuild<RB_THREADS, RB_IPT, false, RB_FINAL><<<tiles, RB_THREADS, 0, st>>>(r);
+      else k_rebuild<RB_THREADS, RB_IPT, false, RB_NORMAL><<<tiles, RB_THREADS, 0, st>>>(r);
+    }
     KLAUNCH_CHECK();
     if (stats) stats->kernel_launches += 3;
     return GSA_OK;
@@ -856,6 +944,8 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
     g.Lin = Lcand; g.rank = y.rank; g.n = n; g.h = h; g.lab_bits = lab_bits; g.npass = npass;
     g.keys_out = y.keys[0]; g.vals_out = y.vals[0]; g.lst_out = y.lst[lcur ^ 1];
     g.counter = y.live_counter; g.ghist = y.ghist;
+    g.sa0 = sparse ? d_SA : nullptr;
+    g.gen = gen;
     const u32 gblocks = (u32)std::min<u64>((u64)sms * GA_BLOCKS_PER_SM, std::max<u64>(1, div_up(Lcand, GA_THREADS * GA_IPT)));
     k_gather<GA_THREADS, GA_IPT, GA_BLOCKS_PER_SM><<<gblocks, GA_THREADS, 0, st>>>(g);
     KLAUNCH_CHECK();

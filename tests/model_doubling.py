@@ -27,7 +27,7 @@ def bits_for(v: int) -> int:
     return b
 
 
-def build_sa_model(text: bytes, log=None, shuffle_seed=None, key_symbols=None) -> np.ndarray:
+def build_sa_model(text: bytes, log=None, shuffle_seed=None, key_symbols=None, sparse=False) -> np.ndarray:
     t = np.frombuffer(bytes(text), dtype=np.uint8)
     n = t.size
     if n == 0:
@@ -56,6 +56,25 @@ def build_sa_model(text: bytes, log=None, shuffle_seed=None, key_symbols=None) -
     SA = np.full(n, -1, np.int64)
     rank = [0] * n
     rng = np.random.default_rng(shuffle_seed) if shuffle_seed is not None else None
+
+    sa0 = list(sufx)  # complete round-0 order (sparse mode keeps it for lazy labels)
+
+    def lazy_label(tpos):
+        """sa_build.cu lazy_label(): slot + 1 of a suffix that was unique after round 0."""
+        kt = keys[tpos]
+        lo, hi = 0, n
+        while lo < hi:
+            mid = (lo + hi) // 2
+            if keys[sa0[mid]] < kt:
+                lo = mid + 1
+            else:
+                hi = mid
+        extra = 0
+        if kt & ((1 << b) - 1) == 0:
+            first_short = n - ns
+            frm = tpos + 1 if tpos >= first_short else first_short
+            extra = sum(1 for j in range(frm, n) if keys[j] == kt)
+        return lo + extra + 1
 
     def rebuild(skey, sufx, pos, round0):
         L = len(sufx)
@@ -86,7 +105,8 @@ def build_sa_model(text: bytes, log=None, shuffle_seed=None, key_symbols=None) -
             if s == e:
                 assert SA[s] == -1
                 SA[s] = sufx[l]
-                rank[sufx[l]] = DEAD | (s + 1)
+                if not (round0 and sparse):
+                    rank[sufx[l]] = DEAD | (s + 1)
                 writes += 1
             else:
                 if not keep:
@@ -100,13 +120,16 @@ def build_sa_model(text: bytes, log=None, shuffle_seed=None, key_symbols=None) -
     h = k
     rounds = 1
     while pos:
-        live = [i for i in lst if not (rank[i] & DEAD)]
+        live = [i for i in lst if rank[i] != 0 and not (rank[i] & DEAD)]
         if rng is not None:
             rng.shuffle(live)  # the order of the sort input is irrelevant
         assert len(live) == len(pos)
         key = []
         for i in live:
             r2 = (rank[i + h] & (DEAD - 1)) if i + h < n else 0
+            if sparse and i + h < n and r2 == 0:
+                r2 = lazy_label(i + h)
+                assert SA[r2 - 1] == i + h  # it really is the final slot of that suffix
             key.append(((rank[i] & (DEAD - 1)) << 31) | r2)
         order = sorted(range(len(live)), key=lambda l: key[l])
         skey = [key[l] for l in order]

@@ -84,6 +84,31 @@ def test_any_round0_depth_gives_the_same_sa(port, monkeypatch):
         monkeypatch.delenv("GSA_KEY_SYMBOLS")
 
 
+def test_sparse_mode_on_and_off(port, monkeypatch):
+    """Few survivors after round 0 -> labels of unique suffixes are recomputed lazily instead of
+    being scattered (RB_SPARSE).  Same SA with the mode disabled; NUL-heavy alphabets exercise the
+    short-suffix correction of lazy_label."""
+    from stringsearch_b200 import synth
+
+    rng = np.random.default_rng(12)
+    texts = [synth.acgt(500_000, 3), synth.random_bytes(300_000, 4), rng.integers(0, 2, 400_000, dtype=np.uint8),
+             np.concatenate([rng.integers(0, 3, 200_000, dtype=np.uint8), np.zeros(40, np.uint8)]),
+             np.concatenate([synth.random_bytes(100_000, 8), synth.random_bytes(100_000, 8)[:50_000]])]
+    for t in texts:
+        exp = port.sa_build(t)
+        for ks in (None, "3", "9"):
+            if ks is None:
+                monkeypatch.delenv("GSA_KEY_SYMBOLS", raising=False)
+            else:
+                monkeypatch.setenv("GSA_KEY_SYMBOLS", ks)
+            monkeypatch.delenv("GSA_NO_SPARSE", raising=False)
+            _assert_same(_sort(t), exp, f"sparse allowed, key_symbols={ks}")
+            monkeypatch.setenv("GSA_NO_SPARSE", "1")
+            _assert_same(_sort(t), exp, f"sparse off, key_symbols={ks}")
+    monkeypatch.delenv("GSA_NO_SPARSE", raising=False)
+    monkeypatch.delenv("GSA_KEY_SYMBOLS", raising=False)
+
+
 def test_tile_boundaries(port):
     """Sizes straddling the radix tile (4096), rebuild tile (2048) and vector widths."""
     rng = np.random.default_rng(7)

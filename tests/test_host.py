@@ -97,6 +97,9 @@ def test_design_model_matches_oracle(port, sa_golden):
         assert (build_sa_model(t, shuffle_seed=i) == port.sa_build(t)).all()
         for ks in (1, 2, 5):  # any round-0 depth must give the same SA
             assert (build_sa_model(t, key_symbols=ks) == port.sa_build(t)).all()
+        # sparse mode: ranks of suffixes unique after round 0 are recomputed lazily
+        assert (build_sa_model(t, sparse=True) == port.sa_build(t)).all()
+        assert (build_sa_model(t, sparse=True, key_symbols=2) == port.sa_build(t)).all()
 
 
 def test_synth_shapes():
