@@ -163,19 +163,20 @@ struct GatherArgs {
   // already unique after round 0; its label is recomputed on demand from the round-0 order.
   const i32 *sa0;  // null unless sparse: SA after round 0, every slot filled
   KeyGen gen;
+  u32 *todo;        // sparse: (output slot, suffix) pairs whose second key half is still missing
+  u32 *todo_count;
 };
 
 // Label of a suffix that was unique after round 0 (sparse mode): its SA slot + 1, found by
 // binary search of its round-0 key in the round-0 order.  Equal keys are ordered short
 // suffixes first (shortest first), then the long ones, so a suffix sits behind every short
 // suffix with the same zero-padded key (and, if short itself, only behind the shorter ones).
-__device__ __noinline__ u32 lazy_label(const GatherArgs &a, u32 t) {
-  const KeyGen &g = a.gen;
+__device__ __forceinline__ u32 lazy_label(const KeyGen &g, const i32 *__restrict__ sa0, u32 t) {
   const u64 kt = key_of_suffix(g, t);
   u32 lo = 0, hi = g.n;
   while (lo < hi) {
     const u32 mid = lo + ((hi - lo) >> 1);
-    if (key_of_suffix(g, (u32)__ldg(a.sa0 + mid)) < kt) lo = mid + 1; else hi = mid;
+    if (key_of_suffix(g, (u32)__ldg(sa0 + mid)) < kt) lo = mid + 1; else hi = mid;
   }
   u32 extra = 0;
   if ((kt & ((1ull << g.b) - 1ull)) == 0ull) {  // only a key ending in symbol 0 can equal a padded one
@@ -218,13 +219,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_gather(const GatherArgs
       const u64 t = (u64)sfx[k] + a.h;
       r2[k] = (!(w[k] & RANK_DEAD) && t < a.n) ? (__ldg(a.rank + t) & RANK_MASK) : 0u;
     }
-    if (a.sa0 != nullptr) {
-#pragma unroll 1
-      for (int k = 0; k < IPT; ++k) {
-        const u64 t = (u64)sfx[k] + a.h;
-        if (!(w[k] & RANK_DEAD) && t < a.n && r2[k] == 0u) r2[k] = lazy_label(a, (u32)t);
-      }
-    }
+
     u32 off[IPT];  // slot offset inside the warp's output run
     u32 wtot = 0;
 #pragma unroll
@@ -253,12 +248,44 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_gather(const GatherArgs
         a.keys_out[o] = ((u64)w[k] << a.lab_bits) | r2[k];
         a.vals_out[o] = sfx[k];
         a.lst_out[o] = sfx[k];
+        if (a.sa0 != nullptr && r2[k] == 0u && (u64)sfx[k] + a.h < a.n) {
+          // sparse mode: suffix i + h has been unique since round 0 and has no stored label;
+          // k_lazy_fill computes it (one binary search per entry, all in flight at once)
+          const u32 q = atomicAdd(a.todo_count, 1u);
+          a.todo[2 * q] = o;
+          a.todo[2 * q + 1] = (u32)(sfx[k] + a.h);
+        }
       }
     }
     __syncthreads();  // s_wcnt / s_base are reused by the next chunk
   }
   for (int i = tid; i < a.npass * RADIX; i += THREADS)
     if (shist[i]) atomicAdd(&a.ghist[i], shist[i]);
+}
+
+// Sparse mode, after k_gather: fill in the missing second key halves, then histogram.
+__global__ void __launch_bounds__(256) k_lazy_fill(const KeyGen g, const i32 *__restrict__ sa0, const u32 *__restrict__ todo,
+                                                   const u32 *__restrict__ todo_count, u64 *__restrict__ keys) {
+  const u32 q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= *todo_count) return;
+  keys[todo[2 * q]] |= (u64)lazy_label(g, sa0, todo[2 * q + 1]);
+}
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) k_hist_keys(const u64 *__restrict__ keys, u32 L, int npass, u32 *__restrict__ ghist) {
+  __shared__ u32 shist[MAX_PASSES * RADIX];
+  for (int i = threadIdx.x; i < npass * RADIX; i += THREADS) shist[i] = 0;
+  __syncthreads();
+  const u32 stride = gridDim.x * THREADS;
+  const u32 iters = (L + stride - 1) / stride;
+  u32 l = blockIdx.x * THREADS + threadIdx.x;
+  for (u32 it = 0; it < iters; ++it, l += stride) {
+    const bool valid = l < L;
+    hist_add(shist, valid ? keys[l] : 0ull, valid, npass);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < npass * RADIX; i += THREADS)
+    if (shist[i]) atomicAdd(&ghist[i], shist[i]);
 }
 
 // ------------------------------------------------------------------------------------
@@ -941,15 +968,28 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
     GSA_TRY(cudaMemsetAsync(y.live_counter, 0, sizeof(u32), st));
     GatherArgs g;
     g.lst_in = ident ? nullptr : y.lst[lcur];
-    g.Lin = Lcand; g.rank = y.rank; g.n = n; g.h = h; g.lab_bits = lab_bits; g.npass = npass;
+    g.Lin = Lcand; g.rank = y.rank; g.n = n; g.h = h; g.lab_bits = lab_bits;
+    g.npass = sparse ? 0 : npass;  // sparse: keys are completed by k_lazy_fill, histogram afterwards
     g.keys_out = y.keys[0]; g.vals_out = y.vals[0]; g.lst_out = y.lst[lcur ^ 1];
     g.counter = y.live_counter; g.ghist = y.ghist;
     g.sa0 = sparse ? d_SA : nullptr;
     g.gen = gen;
+    g.todo = y.pos[pcur ^ 1];  // free until this round's rebuild writes it
+    g.todo_count = y.survivors;
+    if (sparse) GSA_TRY(cudaMemsetAsync(y.survivors, 0, sizeof(u32), st));
     const u32 gblocks = (u32)std::min<u64>((u64)sms * GA_BLOCKS_PER_SM, std::max<u64>(1, div_up(Lcand, GA_THREADS * GA_IPT)));
     k_gather<GA_THREADS, GA_IPT, GA_BLOCKS_PER_SM><<<gblocks, GA_THREADS, 0, st>>>(g);
     KLAUNCH_CHECK();
     if (stats) stats->kernel_launches++;
+    if (sparse) {
+      // at most one entry per live suffix (L of them; L * 64 < n, so the pairs fit in one pos buffer)
+      k_lazy_fill<<<(u32)div_up(L, 256), 256, 0, st>>>(gen, d_SA, g.todo, g.todo_count, y.keys[0]);
+      KLAUNCH_CHECK();
+      const u32 hb = (u32)std::min<u64>((u64)sms * 4, std::max<u64>(1, div_up(L, HIST_THREADS)));
+      k_hist_keys<HIST_THREADS><<<hb, HIST_THREADS, 0, st>>>(y.keys[0], L, npass, y.ghist);
+      KLAUNCH_CHECK();
+      if (stats) stats->kernel_launches += 2;
+    }
     GSA_TRY(cudaEventRecord(ev[1], st));
     GSA_TRY_RC(run_passes(y, L, npass, 0, nullptr, st, stats, timer, &cur, &passes));
     GSA_TRY(cudaEventRecord(ev[2], st));
