@@ -1,0 +1,63 @@
+"""torchrun worker for tests/test_gpu_dist.py: one rank per GPU, NCCL.
+Builds a DistributedPartitionedSuffixArray, runs a collective query, and rank 0 compares the
+result with the oracle's sacapart restatement."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    from stringsearch_b200 import sacapart, synth
+
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    P = int(sys.argv[1]) if len(sys.argv) > 1 else 2 * world
+    text = synth.repetitive(600_000, 31, period=700, mutation_rate=3e-3)  # same bytes on every rank
+    psa = sacapart.DistributedPartitionedSuffixArray(text, P, device=local)
+    assert psa.local_partitions() == list(range(rank, psa.num_partitions(), world))
+    rng = np.random.default_rng(5)
+    needles = None
+    if rank == 0:
+        needles = []
+        ps = len(text) // P + 1
+        for i in range(3000):
+            o = int(rng.integers(0, len(text) - 1))
+            m = int(rng.integers(0, 400))
+            b = bytearray(text[o:o + m].tobytes())
+            if b and i % 3 == 0:
+                b[-1] ^= 0x55
+            needles.append(bytes(b))
+        for i in range(1, P):  # needles straddling partition boundaries (may_extend)
+            needles.append(text[i * ps - 7:i * ps + 200].tobytes())
+    s, l = psa.longest_substring_match_batch(needles)
+    ok = True
+    if rank == 0:
+        from oracle import oracle
+
+        port = oracle.port()
+        ps, sas = port.part_build(text, P)
+        es, el = port.part_lsm_batch(text, ps, sas, needles)
+        ok = bool((s == es).all() and (l == el).all())
+        if not ok:
+            bad = np.flatnonzero((s != es) | (l != el))[:5]
+            print("MISMATCH at", bad, s[bad], es[bad], l[bad], el[bad], flush=True)
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.broadcast(flag, src=0)
+    dist.barrier()
+    dist.destroy_process_group()
+    if rank == 0:
+        print("DIST_OK" if ok else "DIST_FAIL", flush=True)
+    sys.exit(0 if int(flag.item()) == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()
