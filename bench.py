@@ -384,8 +384,8 @@ def bench_queries(dev, device_index):
         d_cnt = torch.empty(Q, dtype=torch.int32, device=dev)
         stream = torch.cuda.current_stream(dev).cuda_stream
         res = {"text": "1 GiB ACGT (seed 5)", "patterns": Q, "pattern_len": m}
-        for name, fn in (("longest_substring_match", lambda: N.lib.gsa_lsm_device(h, d_p.data_ptr(), d_o.data_ptr(), Q, 0, 0, d_s.data_ptr(), d_l.data_ptr(), stream)),
-                         ("search_all", lambda: N.lib.gsa_search_all_device(h, d_p.data_ptr(), d_o.data_ptr(), Q, d_left.data_ptr(), d_cnt.data_ptr(), stream))):
+        for name, fn in (("longest_substring_match", lambda: N.lib.gsa_lsm_device(h, d_p.data_ptr(), d_o.data_ptr(), Q, m, 0, 0, d_s.data_ptr(), d_l.data_ptr(), stream)),
+                         ("search_all", lambda: N.lib.gsa_search_all_device(h, d_p.data_ptr(), d_o.data_ptr(), Q, m, d_left.data_ptr(), d_cnt.data_ptr(), stream))):
             assert fn() == 0
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

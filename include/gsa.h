@@ -149,15 +149,17 @@ int32_t gsa_contains_batch(const gsa_index *ix, const uint8_t *pats, const uint6
                            uint8_t *out);
 
 /* Device-resident forms (all pointers are device pointers on the index's device;
- * results stay on the device; asynchronous on `stream`).  `max_pat_len` bounds
- * pat_off[q+1]-pat_off[q].  For gsa_lsm_device the partition parameters implement
+ * results stay on the device; asynchronous on `stream`).  `max_pat_len` is the longest
+ * pattern of the batch, or 0 if unknown; it only selects how many lanes share a pattern
+ * (8 lanes for <= 32 bytes, 16 for <= 64, else 32) -- results do not depend on it.  For gsa_lsm_device the partition parameters implement
  * sacapart's per-shard step (crates/sacapart/src/lib.rs:71-92): `offset` is added
  * to start, and when `accumulate` != 0 a result only replaces
  * (io_start[q], io_len[q]) if its len is strictly greater. */
 int32_t gsa_lsm_device(const gsa_index *ix, const uint8_t *d_pats, const uint64_t *d_pat_off, uint64_t Q,
-                       uint64_t offset, int32_t accumulate, uint64_t *d_io_start, uint32_t *d_io_len, void *stream);
+                       uint32_t max_pat_len, uint64_t offset, int32_t accumulate, uint64_t *d_io_start,
+                       uint32_t *d_io_len, void *stream);
 int32_t gsa_search_all_device(const gsa_index *ix, const uint8_t *d_pats, const uint64_t *d_pat_off, uint64_t Q,
-                              int32_t *d_out_left, int32_t *d_out_count, void *stream);
+                              uint32_t max_pat_len, int32_t *d_out_left, int32_t *d_out_count, void *stream);
 
 /* Merge step of a fanned-out partitioned query: for every q keep the longer match;
  * on equal length keep the one with the smaller start (= lower partition index,

@@ -103,8 +103,8 @@ def _load() -> C.CDLL:
         "gsa_lsm_batch": ([vp, vp, vp, C.c_uint64, vp, vp], C.c_int32),
         "gsa_search_all_batch": ([vp, vp, vp, C.c_uint64, vp, vp], C.c_int32),
         "gsa_contains_batch": ([vp, vp, vp, C.c_uint64, vp], C.c_int32),
-        "gsa_lsm_device": ([vp, vp, vp, C.c_uint64, C.c_uint64, C.c_int32, vp, vp, vp], C.c_int32),
-        "gsa_search_all_device": ([vp, vp, vp, C.c_uint64, vp, vp, vp], C.c_int32),
+        "gsa_lsm_device": ([vp, vp, vp, C.c_uint64, C.c_uint32, C.c_uint64, C.c_int32, vp, vp, vp], C.c_int32),
+        "gsa_search_all_device": ([vp, vp, vp, C.c_uint64, C.c_uint32, vp, vp, vp], C.c_int32),
         "gsa_lsm_reduce_device": ([vp, vp, C.c_uint64, C.c_uint32, vp], C.c_int32),
         "gsa_part_create": ([vp, C.c_uint64, C.c_uint64, i32p, C.c_int32, C.POINTER(vp)], C.c_int32),
         "gsa_part_num_partitions": ([vp], C.c_uint64),

@@ -395,6 +395,12 @@ struct PatternsOnDevice {
   }
 };
 
+static u32 max_len(const u64 *pat_off, u64 Q) {
+  u64 m = 0;
+  for (u64 q = 0; q < Q; ++q) m = std::max(m, pat_off[q + 1] - pat_off[q]);
+  return (u32)std::min<u64>(m, 0xffffffffull);
+}
+
 static int check_patterns(const u8 *pats, const u64 *pat_off, u64 Q) {
   if (Q == 0) return GSA_OK;
   if (!pat_off) return GSA_EINVAL;
@@ -418,7 +424,7 @@ int32_t gsa_lsm_batch(const gsa_index *ix, const uint8_t *pats, const uint64_t *
   DevBuf<u32> d_len;
   GSA_TRY_RC(d_start.alloc((size_t)Q));
   GSA_TRY_RC(d_len.alloc((size_t)Q));
-  GSA_TRY_RC(lsm_device(view_of(ix), pd.pats.p, pd.off.p, Q, 0, 0, d_start.p, d_len.p, st.s));
+  GSA_TRY_RC(lsm_device(view_of(ix), pd.pats.p, pd.off.p, Q, max_len(pat_off, Q), 0, 0, d_start.p, d_len.p, st.s));
   GSA_TRY(cudaMemcpyAsync(out_start, d_start.p, (size_t)Q * 8, cudaMemcpyDeviceToHost, st.s));
   GSA_TRY(cudaMemcpyAsync(out_len, d_len.p, (size_t)Q * 4, cudaMemcpyDeviceToHost, st.s));
   GSA_TRY(cudaStreamSynchronize(st.s));
@@ -443,7 +449,7 @@ int32_t gsa_search_all_batch(const gsa_index *ix, const uint8_t *pats, const uin
   DevBuf<i32> d_left, d_count;
   GSA_TRY_RC(d_left.alloc((size_t)Q));
   GSA_TRY_RC(d_count.alloc((size_t)Q));
-  GSA_TRY_RC(search_all_device(view_of(ix), pd.pats.p, pd.off.p, Q, d_left.p, d_count.p, st.s));
+  GSA_TRY_RC(search_all_device(view_of(ix), pd.pats.p, pd.off.p, Q, max_len(pat_off, Q), d_left.p, d_count.p, st.s));
   GSA_TRY(cudaMemcpyAsync(out_left, d_left.p, (size_t)Q * 4, cudaMemcpyDeviceToHost, st.s));
   GSA_TRY(cudaMemcpyAsync(out_count, d_count.p, (size_t)Q * 4, cudaMemcpyDeviceToHost, st.s));
   GSA_TRY(cudaStreamSynchronize(st.s));
@@ -460,17 +466,18 @@ int32_t gsa_contains_batch(const gsa_index *ix, const uint8_t *pats, const uint6
 }
 
 int32_t gsa_lsm_device(const gsa_index *ix, const uint8_t *d_pats, const uint64_t *d_pat_off, uint64_t Q,
-                       uint64_t offset, int32_t accumulate, uint64_t *d_io_start, uint32_t *d_io_len, void *stream) {
+                       uint32_t max_pat_len, uint64_t offset, int32_t accumulate, uint64_t *d_io_start,
+                       uint32_t *d_io_len, void *stream) {
   if (!ix || (Q > 0 && (!d_pat_off || !d_io_start || !d_io_len))) return GSA_EINVAL;
-  return lsm_device(view_of(ix), d_pats, d_pat_off, Q, offset, accumulate, d_io_start, d_io_len,
+  return lsm_device(view_of(ix), d_pats, d_pat_off, Q, max_pat_len, offset, accumulate, d_io_start, d_io_len,
                     static_cast<cudaStream_t>(stream));
 }
 
 int32_t gsa_search_all_device(const gsa_index *ix, const uint8_t *d_pats, const uint64_t *d_pat_off, uint64_t Q,
-                              int32_t *d_out_left, int32_t *d_out_count, void *stream) {
+                              uint32_t max_pat_len, int32_t *d_out_left, int32_t *d_out_count, void *stream) {
   if (!ix || (Q > 0 && (!d_pat_off || !d_out_left || !d_out_count))) return GSA_EINVAL;
   if (ix->n == 0) return GSA_EINVAL;
-  return search_all_device(view_of(ix), d_pats, d_pat_off, Q, d_out_left, d_out_count,
+  return search_all_device(view_of(ix), d_pats, d_pat_off, Q, max_pat_len, d_out_left, d_out_count,
                            static_cast<cudaStream_t>(stream));
 }
 
@@ -583,7 +590,7 @@ int32_t gsa_part_lsm_batch(gsa_part *p, const uint8_t *pats, const uint64_t *pat
     for (size_t i = k; i < p->shards.size(); i += nd) {
       gsa_index *ix = p->shards[i];
       GSA_TRY_RC(ensure_halo(ix, max_len));
-      GSA_TRY_RC(lsm_device(view_of(ix), d.pd.pats.p, d.pd.off.p, Q, ix->offset, first ? 0 : 1, d.start.p, d.len.p,
+      GSA_TRY_RC(lsm_device(view_of(ix), d.pd.pats.p, d.pd.off.p, Q, (u32)std::min<u64>(max_len, 0xffffffffull), ix->offset, first ? 0 : 1, d.start.p, d.len.p,
                             d.st.s));
       first = false;
     }

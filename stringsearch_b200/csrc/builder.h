@@ -29,10 +29,11 @@ struct TextView {
   u64 n;
   u64 text_avail;
 };
-int lsm_device(const TextView &tv, const u8 *d_pats, const u64 *d_pat_off, u64 Q, u64 offset, int accumulate,
-               u64 *d_io_start, u32 *d_io_len, cudaStream_t st);
-int search_all_device(const TextView &tv, const u8 *d_pats, const u64 *d_pat_off, u64 Q, i32 *d_left, i32 *d_count,
-                      cudaStream_t st);
+// max_pat_len: longest pattern of the batch, or 0 if unknown (only picks the lanes-per-pattern variant)
+int lsm_device(const TextView &tv, const u8 *d_pats, const u64 *d_pat_off, u64 Q, u32 max_pat_len, u64 offset,
+               int accumulate, u64 *d_io_start, u32 *d_io_len, cudaStream_t st);
+int search_all_device(const TextView &tv, const u8 *d_pats, const u64 *d_pat_off, u64 Q, u32 max_pat_len, i32 *d_left,
+                      i32 *d_count, cudaStream_t st);
 int lsm_reduce_device(u64 *d_start, u32 *d_len, u64 Q, u32 nsets, cudaStream_t st);
 
 }  // namespace gsa

@@ -1,5 +1,5 @@
-// search.cu -- batched suffix-array search kernels: one warp per pattern, warp-cooperative
-// byte comparison against text resident in HBM.
+// search.cu -- batched suffix-array search kernels: a group of 8/16/32 lanes per pattern,
+// cooperative word comparison against text resident in HBM.
 //
 //   k_lsm         sacabase::longest_substring_match (reference:
 //                 crates/sacabase/src/lib.rs:39-99) with sacapart's per-shard step
@@ -15,8 +15,14 @@
 
 namespace gsa {
 
-// Compares pattern P[0,m) with the text bytes [s, tend), starting at byte `from` (the first
-// `from` bytes are known to be equal).  Warp-cooperative; every lane returns the same values.
+// A pattern is handled by a group of G lanes (G = 8, 16 or 32, chosen from the longest pattern
+// of the batch: 4 bytes per lane and step, so G = 8 covers 32-byte patterns in one step and a
+// warp carries 4 independent binary searches -- the walk is latency bound, more searches in
+// flight is what makes it faster).  All lanes of the warp run in lockstep; a group whose search
+// has finished idles until the others are done.
+//
+// group_compare: pattern P[0,m) against the text bytes [s, tend), the first `from` bytes being
+// known equal.  Every lane of the group returns the same values.
 //   cpl = length of the common prefix (<= min(m, tend - s))
 //   gt  = pattern > suffix in Rust slice order / sa_search's r < 0
 //         (first differing byte larger, or the suffix is a proper prefix of the pattern)
@@ -27,33 +33,58 @@ struct CmpResult {
   bool lt;
 };
 
-__device__ __forceinline__ CmpResult warp_compare(const u8 *__restrict__ text, u64 s, u64 tend,
-                                                  const u8 *__restrict__ pat, u32 m, u32 pat_lane0, u32 from) {
+// The nb (1..4) bytes at an arbitrary address as a little-endian word, from aligned 4-byte
+// loads.  Only words that contain at least one of the requested bytes are touched, so no
+// padding behind the buffers is required.
+__device__ __forceinline__ u32 load_bytes(const u8 *p, u32 nb) {
+  const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+  const u32 *w = reinterpret_cast<const u32 *>(a & ~(uintptr_t)3);
+  const u32 mis = (u32)(a & 3u);
+  const u32 lo = __ldg(w);
+  if (mis + nb <= 4u) return lo >> (8u * mis);
+  return __funnelshift_r(lo, __ldg(w + 1), 8u * mis);
+}
+
+template <int G>
+__device__ __forceinline__ CmpResult group_compare(const u8 *__restrict__ text, u64 s, u64 tend,
+                                                   const u8 *__restrict__ pat, u32 m, u32 pat_word0, u32 from, bool active) {
   const u32 lane = lane_id();
+  const u32 sub = lane & (G - 1);              // lane inside the group
+  const u32 gshift = lane & ~(u32)(G - 1);     // first lane of the group
+  const u32 gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << gshift);
   const u64 rem = tend - s;
   const u32 lim = (rem < (u64)m) ? (u32)rem : m;
   CmpResult r;
-  for (u32 off = from & ~31u; off < lim; off += 32) {
-    const u32 i = off + lane;
-    u32 pb = 0, tb = 0;
-    if (i < lim) {
-      pb = (off == 0) ? pat_lane0 : (u32)__ldg(pat + i);
-      tb = (u32)__ldg(text + s + i);
+  r.cpl = lim;
+  r.gt = m > lim;  // no difference found: the suffix is a proper prefix of the pattern, or equal
+  r.lt = false;
+  bool done = !active;
+  for (u32 off = from & ~(4u * G - 1u); ; off += 4u * G) {
+    const bool run = !done && off < lim;
+    if (!__any_sync(0xffffffffu, run)) break;
+    u32 neq = 0, pw = 0, tw = 0;
+    const u32 i = off + 4u * sub;
+    if (run && i < lim) {
+      const u32 nb = min(4u, lim - i);
+      pw = (off == 0) ? pat_word0 : load_bytes(pat + i, nb);
+      tw = load_bytes(text + s + i, nb);
+      neq = (pw ^ tw) & ((nb == 4u) ? 0xffffffffu : ((1u << (8u * nb)) - 1u));
     }
-    const u32 neq = __ballot_sync(0xffffffffu, pb != tb);
-    if (neq) {
-      const int first = __ffs(neq) - 1;
-      r.cpl = off + (u32)first;
-      const u32 p1 = __shfl_sync(0xffffffffu, pb, first);
-      const u32 t1 = __shfl_sync(0xffffffffu, tb, first);
-      r.gt = p1 > t1;
-      r.lt = p1 < t1;
-      return r;
+    const u32 bal = __ballot_sync(0xffffffffu, neq != 0u) & gmask;
+    // every lane takes part in the shuffles (full mask); groups without a difference read themselves
+    const u32 first = bal ? ((u32)__ffs(bal) - 1u) : lane;  // absolute lane holding the first difference
+    const u32 fn = __shfl_sync(0xffffffffu, neq, first);
+    const u32 fp = __shfl_sync(0xffffffffu, pw, first);
+    const u32 ft = __shfl_sync(0xffffffffu, tw, first);
+    if (run && bal) {
+      const u32 byte = ((u32)__ffs(fn) - 1u) >> 3;
+      const u32 pb = (fp >> (8u * byte)) & 255u, tb = (ft >> (8u * byte)) & 255u;
+      r.cpl = off + 4u * (first - gshift) + byte;
+      r.gt = pb > tb;
+      r.lt = pb < tb;
+      done = true;
     }
   }
-  r.cpl = lim;
-  r.gt = m > lim;  // text ran out first: the suffix is a proper prefix of the pattern
-  r.lt = false;
   return r;
 }
 
@@ -71,33 +102,50 @@ struct LsmArgs {
   u32 *io_len;
 };
 
+template <int G>
 __global__ void __launch_bounds__(256) k_lsm(const LsmArgs a) {
-  const u64 q = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (q >= a.Q) return;
+  constexpr int PER_WARP = 32 / G;
   const u32 lane = lane_id();
-  const u64 p0 = a.pat_off[q];
-  const u32 m = (u32)(a.pat_off[q + 1] - p0);
+  const u64 warp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const u64 q = warp * PER_WARP + (lane / G);
+  const bool have = q < a.Q;
+  const u32 sub = lane & (G - 1);
+  u64 p0 = 0;
+  u32 m = 0;
+  if (have) {
+    p0 = a.pat_off[q];
+    m = (u32)(a.pat_off[q + 1] - p0);
+  }
   const u8 *pat = a.pats + p0;
-  const u32 pl0 = (lane < m) ? (u32)__ldg(pat + lane) : 0u;
+  const u32 pw0 = (have && 4u * sub < m) ? load_bytes(pat + 4u * sub, min(4u, m - 4u * sub)) : 0u;
 
   // sacabase lib.rs:75-98 on the window sa[lo .. lo+w)
   u64 lo = 0, w = a.n;
-  while (w > 2) {
+  for (;;) {
+    const bool act = have && w > 2;
+    if (!__any_sync(0xffffffffu, act)) break;
     const u64 mid = w >> 1;
-    const u64 s = (u64)(u32)__ldg(a.sa + lo + mid);
-    const CmpResult c = warp_compare(a.text, s, a.n, pat, m, pl0, 0);
-    if (c.gt) { lo += mid; w -= mid; } else { w = mid + 1; }
+    const u64 s = act ? (u64)(u32)__ldg(a.sa + lo + mid) : 0;
+    const CmpResult c = group_compare<G>(a.text, s, a.n, pat, m, pw0, 0, act);
+    if (act) {
+      if (c.gt) { lo += mid; w -= mid; } else { w = mid + 1; }
+    }
   }
-  u64 start = (u64)(u32)__ldg(a.sa + lo);
-  u32 len = warp_compare(a.text, start, a.n, pat, m, pl0, 0).cpl;
-  if (w == 2) {
-    const u64 s1 = (u64)(u32)__ldg(a.sa + lo + 1);
-    const u32 y = warp_compare(a.text, s1, a.n, pat, m, pl0, 0).cpl;
-    if (!(len > y)) { start = s1; len = y; }  // `x > y` keeps the first, ties go to the second
+  u64 start = have ? (u64)(u32)__ldg(a.sa + lo) : 0;
+  u32 len = group_compare<G>(a.text, start, a.n, pat, m, pw0, 0, have).cpl;
+  {
+    const bool two = have && w == 2;
+    const u64 s1 = two ? (u64)(u32)__ldg(a.sa + lo + 1) : 0;
+    const u32 y = group_compare<G>(a.text, s1, a.n, pat, m, pw0, 0, two).cpl;
+    if (two && !(len > y)) { start = s1; len = y; }  // `x > y` keeps the first, ties go to the second
   }
-  // sacapart lib.rs:77-84: a match that touches the end of the shard may continue behind it
-  if (start + len == a.n && a.text_avail > a.n) len = warp_compare(a.text, start, a.text_avail, pat, m, pl0, len).cpl;
-  if (lane == 0) {
+  {
+    // sacapart lib.rs:77-84: a match that touches the end of the shard may continue behind it
+    const bool ext = have && start + len == a.n && a.text_avail > a.n;
+    const u32 l2 = group_compare<G>(a.text, start, a.text_avail, pat, m, pw0, len, ext).cpl;
+    if (ext) len = l2;
+  }
+  if (have && sub == 0) {
     if (!a.accumulate || len > a.io_len[q]) {  // lib.rs:86-92, strict
       a.io_start[q] = start + a.offset;
       a.io_len[q] = len;
@@ -116,34 +164,48 @@ struct SearchAllArgs {
   i32 *count;
 };
 
+template <int G>
 __global__ void __launch_bounds__(256) k_search_all(const SearchAllArgs a) {
-  const u64 q = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (q >= a.Q) return;
+  constexpr int PER_WARP = 32 / G;
   const u32 lane = lane_id();
-  const u64 p0 = a.pat_off[q];
-  const u32 m = (u32)(a.pat_off[q + 1] - p0);
-  if (m == 0) {  // utils.c:273
-    if (lane == 0) { a.left[q] = 0; a.count[q] = (i32)a.n; }
-    return;
+  const u64 warp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const u64 q = warp * PER_WARP + (lane / G);
+  const u32 sub = lane & (G - 1);
+  bool have = q < a.Q;
+  u64 p0 = 0;
+  u32 m = 0;
+  if (have) {
+    p0 = a.pat_off[q];
+    m = (u32)(a.pat_off[q + 1] - p0);
+  }
+  if (have && m == 0) {  // utils.c:273
+    if (sub == 0) { a.left[q] = 0; a.count[q] = (i32)a.n; }
+    have = false;
   }
   const u8 *pat = a.pats + p0;
-  const u32 pl0 = (lane < m) ? (u32)__ldg(pat + lane) : 0u;
+  const u32 pw0 = (have && 4u * sub < m) ? load_bytes(pat + 4u * sub, min(4u, m - 4u * sub)) : 0u;
   // lower bound: suffixes with r < 0   (suffix < pattern)
   u64 lo = 0, hi = a.n;
-  while (lo < hi) {
+  for (;;) {
+    const bool act = have && lo < hi;
+    if (!__any_sync(0xffffffffu, act)) break;
     const u64 mid = (lo + hi) >> 1;
-    const CmpResult c = warp_compare(a.text, (u64)(u32)__ldg(a.sa + mid), a.n, pat, m, pl0, 0);
-    if (c.gt) lo = mid + 1; else hi = mid;
+    const u64 s = act ? (u64)(u32)__ldg(a.sa + mid) : 0;
+    const CmpResult c = group_compare<G>(a.text, s, a.n, pat, m, pw0, 0, act);
+    if (act) { if (c.gt) lo = mid + 1; else hi = mid; }
   }
   const u64 left = lo;
   // upper bound: suffixes with r <= 0  (suffix < pattern, or pattern is a prefix of it)
   hi = a.n;
-  while (lo < hi) {
+  for (;;) {
+    const bool act = have && lo < hi;
+    if (!__any_sync(0xffffffffu, act)) break;
     const u64 mid = (lo + hi) >> 1;
-    const CmpResult c = warp_compare(a.text, (u64)(u32)__ldg(a.sa + mid), a.n, pat, m, pl0, 0);
-    if (!c.lt) lo = mid + 1; else hi = mid;
+    const u64 s = act ? (u64)(u32)__ldg(a.sa + mid) : 0;
+    const CmpResult c = group_compare<G>(a.text, s, a.n, pat, m, pw0, 0, act);
+    if (act) { if (!c.lt) lo = mid + 1; else hi = mid; }
   }
-  if (lane == 0) {
+  if (have && sub == 0) {
     a.left[q] = (i32)left;  // first match, or the insertion point on a miss (utils.c:323)
     a.count[q] = (i32)(lo - left);
   }
@@ -163,23 +225,36 @@ __global__ void __launch_bounds__(256) k_lsm_reduce(u64 *__restrict__ start, u32
   len[q] = bl;
 }
 
-int lsm_device(const TextView &tv, const u8 *d_pats, const u64 *d_pat_off, u64 Q, u64 offset, int accumulate,
-               u64 *d_io_start, u32 *d_io_len, cudaStream_t st) {
+static int group_lanes(u32 max_pat_len) {
+  if (max_pat_len == 0 || max_pat_len > 64) return 32;  // unknown or long: 128 bytes per step
+  return max_pat_len > 32 ? 16 : 8;
+}
+
+int lsm_device(const TextView &tv, const u8 *d_pats, const u64 *d_pat_off, u64 Q, u32 max_pat_len, u64 offset,
+               int accumulate, u64 *d_io_start, u32 *d_io_len, cudaStream_t st) {
   if (Q == 0) return GSA_OK;
   if (tv.n == 0) return GSA_EPANIC;  // sacabase lib.rs:89-91 indexes sa[0]
   LsmArgs a{tv.text, tv.sa, tv.n, tv.text_avail, d_pats, d_pat_off, Q, offset, accumulate, d_io_start, d_io_len};
-  const u64 blocks = div_up(Q * 32, 256);
-  k_lsm<<<(unsigned)blocks, 256, 0, st>>>(a);
+  const int G = group_lanes(max_pat_len);
+  const u64 warps = div_up(Q, 32 / G);
+  const unsigned blocks = (unsigned)div_up(warps * 32, 256);
+  if (G == 8) k_lsm<8><<<blocks, 256, 0, st>>>(a);
+  else if (G == 16) k_lsm<16><<<blocks, 256, 0, st>>>(a);
+  else k_lsm<32><<<blocks, 256, 0, st>>>(a);
   GSA_TRY(cudaGetLastError());
   return GSA_OK;
 }
 
-int search_all_device(const TextView &tv, const u8 *d_pats, const u64 *d_pat_off, u64 Q, i32 *d_left, i32 *d_count,
-                      cudaStream_t st) {
+int search_all_device(const TextView &tv, const u8 *d_pats, const u64 *d_pat_off, u64 Q, u32 max_pat_len, i32 *d_left,
+                      i32 *d_count, cudaStream_t st) {
   if (Q == 0) return GSA_OK;
   SearchAllArgs a{tv.text, tv.sa, tv.n, d_pats, d_pat_off, Q, d_left, d_count};
-  const u64 blocks = div_up(Q * 32, 256);
-  k_search_all<<<(unsigned)blocks, 256, 0, st>>>(a);
+  const int G = group_lanes(max_pat_len);
+  const u64 warps = div_up(Q, 32 / G);
+  const unsigned blocks = (unsigned)div_up(warps * 32, 256);
+  if (G == 8) k_search_all<8><<<blocks, 256, 0, st>>>(a);
+  else if (G == 16) k_search_all<16><<<blocks, 256, 0, st>>>(a);
+  else k_search_all<32><<<blocks, 256, 0, st>>>(a);
   GSA_TRY(cudaGetLastError());
   return GSA_OK;
 }

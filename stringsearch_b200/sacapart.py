@@ -133,14 +133,14 @@ class DistributedPartitionedSuffixArray(StringIndex):
         N.check(rc, "gsa_index_create_shard")
         return h
 
-    def _answer_local(self, t_pat, t_off, q, t_start, t_len, dev) -> None:
+    def _answer_local(self, t_pat, t_off, q, t_start, t_len, dev, max_len: int = 0) -> None:
         import torch
 
         if not torch.cuda.is_available():
             raise RuntimeError("stringsearch_b200 has no CPU path: shards need a CUDA device")
         stream = torch.cuda.current_stream(dev).cuda_stream
         for k, (_, offset, h) in enumerate(self._shards):
-            rc = N.lib.gsa_lsm_device(h, t_pat.data_ptr(), t_off.data_ptr(), q, offset, 0 if k == 0 else 1,
+            rc = N.lib.gsa_lsm_device(h, t_pat.data_ptr(), t_off.data_ptr(), q, max_len, offset, 0 if k == 0 else 1,
                                       t_start.data_ptr(), t_len.data_ptr(), stream)
             N.check(rc, "gsa_lsm_device")
 
@@ -188,7 +188,7 @@ class DistributedPartitionedSuffixArray(StringIndex):
         t_start = torch.zeros(q, dtype=torch.int64, device=dev)
         t_len = torch.zeros(q, dtype=torch.int32, device=dev)
         if self._shards:
-            self._answer_local(t_pat, t_off, q, t_start, t_len, dev)
+            self._answer_local(t_pat, t_off, q, t_start, t_len, dev, max_len)
         else:
             t_start.fill_(2**62)  # a rank without shards never wins (len 0, huge start)
         # ---- gather + merge ---------------------------------------------------------------------

@@ -32,7 +32,7 @@ def _worker(rank, world, port_no, text_bytes, P, needles, expect, q):
         def _destroy_shard(self, h):
             pass
 
-        def _answer_local(self, t_pat, t_off, qn, t_start, t_len, dev):
+        def _answer_local(self, t_pat, t_off, qn, t_start, t_len, dev, max_len=0):
             pats = t_pat.numpy()
             off = t_off.numpy()
             for k, (_, offset, (o, ln, sa)) in enumerate(self._shards):
