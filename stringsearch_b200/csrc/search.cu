@@ -119,16 +119,24 @@ __global__ void __launch_bounds__(256) k_lsm(const LsmArgs a) {
   const u8 *pat = a.pats + p0;
   const u32 pw0 = (have && 4u * sub < m) ? load_bytes(pat + 4u * sub, min(4u, m - 4u * sub)) : 0u;
 
-  // sacabase lib.rs:75-98 on the window sa[lo .. lo+w)
+  // sacabase lib.rs:75-98 on the window sa[lo .. lo+w).  The SA entries probed by BOTH possible
+  // next windows are requested before the comparison of the current one, so a step costs one
+  // dependent memory round trip (the text read) instead of two.
   u64 lo = 0, w = a.n;
+  u64 s_cur = (have && w > 2) ? (u64)(u32)__ldg(a.sa + (w >> 1)) : 0;
   for (;;) {
     const bool act = have && w > 2;
     if (!__any_sync(0xffffffffu, act)) break;
     const u64 mid = w >> 1;
-    const u64 s = act ? (u64)(u32)__ldg(a.sa + lo + mid) : 0;
-    const CmpResult c = group_compare<G>(a.text, s, a.n, pat, m, pw0, 0, act);
+    const u64 wl = mid + 1, wr = w - mid;  // window sizes after going left / right
+    u64 sl = 0, sr = 0;
     if (act) {
-      if (c.gt) { lo += mid; w -= mid; } else { w = mid + 1; }
+      if (wl > 2) sl = (u64)(u32)__ldg(a.sa + lo + (wl >> 1));
+      if (wr > 2) sr = (u64)(u32)__ldg(a.sa + lo + mid + (wr >> 1));
+    }
+    const CmpResult c = group_compare<G>(a.text, s_cur, a.n, pat, m, pw0, 0, act);
+    if (act) {
+      if (c.gt) { lo += mid; w = wr; s_cur = sr; } else { w = wl; s_cur = sl; }
     }
   }
   u64 start = have ? (u64)(u32)__ldg(a.sa + lo) : 0;
@@ -184,27 +192,23 @@ __global__ void __launch_bounds__(256) k_search_all(const SearchAllArgs a) {
   }
   const u8 *pat = a.pats + p0;
   const u32 pw0 = (have && 4u * sub < m) ? load_bytes(pat + 4u * sub, min(4u, m - 4u * sub)) : 0u;
-  // lower bound: suffixes with r < 0   (suffix < pattern)
-  u64 lo = 0, hi = a.n;
+  // lower bound L: suffixes with r < 0 (suffix < pattern); upper bound U: suffixes with r <= 0
+  // (suffix < pattern, or pattern is a prefix of it).  The two binary searches are independent
+  // and are advanced together, so their memory round trips overlap.
+  u64 lo = 0, hi = a.n, lo2 = 0, hi2 = a.n;
   for (;;) {
-    const bool act = have && lo < hi;
-    if (!__any_sync(0xffffffffu, act)) break;
-    const u64 mid = (lo + hi) >> 1;
-    const u64 s = act ? (u64)(u32)__ldg(a.sa + mid) : 0;
-    const CmpResult c = group_compare<G>(a.text, s, a.n, pat, m, pw0, 0, act);
-    if (act) { if (c.gt) lo = mid + 1; else hi = mid; }
+    const bool act1 = have && lo < hi, act2 = have && lo2 < hi2;
+    if (!__any_sync(0xffffffffu, act1 || act2)) break;
+    const u64 mid1 = (lo + hi) >> 1, mid2 = (lo2 + hi2) >> 1;
+    const u64 s1 = act1 ? (u64)(u32)__ldg(a.sa + mid1) : 0;
+    const u64 s2 = act2 ? (u64)(u32)__ldg(a.sa + mid2) : 0;
+    const CmpResult c1 = group_compare<G>(a.text, s1, a.n, pat, m, pw0, 0, act1);
+    const CmpResult c2 = group_compare<G>(a.text, s2, a.n, pat, m, pw0, 0, act2);
+    if (act1) { if (c1.gt) lo = mid1 + 1; else hi = mid1; }
+    if (act2) { if (!c2.lt) lo2 = mid2 + 1; else hi2 = mid2; }
   }
   const u64 left = lo;
-  // upper bound: suffixes with r <= 0  (suffix < pattern, or pattern is a prefix of it)
-  hi = a.n;
-  for (;;) {
-    const bool act = have && lo < hi;
-    if (!__any_sync(0xffffffffu, act)) break;
-    const u64 mid = (lo + hi) >> 1;
-    const u64 s = act ? (u64)(u32)__ldg(a.sa + mid) : 0;
-    const CmpResult c = group_compare<G>(a.text, s, a.n, pat, m, pw0, 0, act);
-    if (act) { if (!c.lt) lo = mid + 1; else hi = mid; }
-  }
+  lo = lo2;
   if (have && sub == 0) {
     a.left[q] = (i32)left;  // first match, or the insertion point on a miss (utils.c:323)
     a.count[q] = (i32)(lo - left);
