@@ -119,24 +119,18 @@ __global__ void __launch_bounds__(256) k_lsm(const LsmArgs a) {
   const u8 *pat = a.pats + p0;
   const u32 pw0 = (have && 4u * sub < m) ? load_bytes(pat + 4u * sub, min(4u, m - 4u * sub)) : 0u;
 
-  // sacabase lib.rs:75-98 on the window sa[lo .. lo+w).  The SA entries probed by BOTH possible
-  // next windows are requested before the comparison of the current one, so a step costs one
-  // dependent memory round trip (the text read) instead of two.
+  // sacabase lib.rs:75-98 on the window sa[lo .. lo+w).  (Requesting the SA entries of both
+  // possible next windows ahead of the comparison was tried and does not pay: at 1 GiB the walk
+  // is bound by the rate of random DRAM sector fetches, not by their latency.)
   u64 lo = 0, w = a.n;
-  u64 s_cur = (have && w > 2) ? (u64)(u32)__ldg(a.sa + (w >> 1)) : 0;
   for (;;) {
     const bool act = have && w > 2;
     if (!__any_sync(0xffffffffu, act)) break;
     const u64 mid = w >> 1;
-    const u64 wl = mid + 1, wr = w - mid;  // window sizes after going left / right
-    u64 sl = 0, sr = 0;
+    const u64 s = act ? (u64)(u32)__ldg(a.sa + lo + mid) : 0;
+    const CmpResult c = group_compare<G>(a.text, s, a.n, pat, m, pw0, 0, act);
     if (act) {
-      if (wl > 2) sl = (u64)(u32)__ldg(a.sa + lo + (wl >> 1));
-      if (wr > 2) sr = (u64)(u32)__ldg(a.sa + lo + mid + (wr >> 1));
-    }
-    const CmpResult c = group_compare<G>(a.text, s_cur, a.n, pat, m, pw0, 0, act);
-    if (act) {
-      if (c.gt) { lo += mid; w = wr; s_cur = sr; } else { w = wl; s_cur = sl; }
+      if (c.gt) { lo += mid; w -= mid; } else { w = mid + 1; }
     }
   }
   u64 start = have ? (u64)(u32)__ldg(a.sa + lo) : 0;
