@@ -302,7 +302,7 @@ def run_ours(args, rank, local_rank, world):
             "share_of_step": pass_ms / ms if ms > 0 else None,
             "whole_build": {"algorithmic_bytes": int(alg_bytes), "achieved": alg_bytes * args.steps / (ms / 1e3) / 1e9,
                             "frac_of_peak": alg_bytes * args.steps / (ms / 1e3) / 1e9 / peak,
-                            "formula": "round0 n(41+24p) + sum_k L_k(52+24p_k), SURVEY.md 8(d)"},
+                            "formula": "round0 n(41+24p0) + sum_k (52 L_k + 24 p_k S_k), S_k <= L_k suffixes actually sorted (SURVEY.md 8(d))"},
         },
         "rounds": rounds_log,
     }

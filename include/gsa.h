@@ -43,14 +43,14 @@ extern "C" {
 
 /* Per-round log of one SA construction (one entry per prefix-doubling round).
  * The harness uses it to recompute the roofline:
- * algorithmic bytes of round k = live * (52 + 24 * passes) (round 0: n * (41 + 24 * passes)). */
+ * algorithmic bytes of round k = live * 52 + sorted * 24 * passes (round 0: n * (41 + 24 * passes)). */
 typedef struct gsa_round_stat {
   uint64_t depth;      /* symbols of every suffix known to be sorted AFTER this round */
-  uint64_t live;       /* suffixes processed (sorted) in this round */
-  uint32_t groups;     /* unsorted groups entering the round (0 for round 0) */
+  uint64_t live;       /* live (not yet unique) suffixes walked in this round */
+  uint32_t groups;     /* huge groups handled through the group tables in this round */
   uint32_t key_bits;   /* significant bits of the sort key */
   uint32_t passes;     /* 8-bit radix passes actually executed */
-  uint32_t reserved;
+  uint32_t sorted;     /* suffixes actually sorted (live minus the inert members of huge groups) */
   float ms_total;      /* device time of the whole round */
   float ms_sort;       /* ... of which radix passes */
 } gsa_round_stat;

@@ -30,7 +30,7 @@ class RoundStat(C.Structure):
         ("groups", C.c_uint32),
         ("key_bits", C.c_uint32),
         ("passes", C.c_uint32),
-        ("reserved", C.c_uint32),
+        ("sorted", C.c_uint32),
         ("ms_total", C.c_float),
         ("ms_sort", C.c_float),
     ]
@@ -54,16 +54,20 @@ class BuildStats(C.Structure):
 
     def rounds_list(self):
         return [
-            dict(depth=int(r.depth), live=int(r.live), groups=int(r.groups), key_bits=int(r.key_bits),
+            dict(depth=int(r.depth), live=int(r.live), sorted=int(r.sorted), groups=int(r.groups), key_bits=int(r.key_bits),
                  passes=int(r.passes), ms_total=float(r.ms_total), ms_sort=float(r.ms_sort))
             for r in list(self.round)[: min(self.rounds, GSA_MAX_ROUNDS)]
         ]
 
     def algorithmic_bytes(self) -> int:
-        """round 0 n*(41+24p), round k>=1 L*(52+24p)."""
+        """round 0 n*(41+24p); round k>=1 L*52 + S*24p, where S <= L is the
+        number of suffixes actually sorted (inert members of huge groups are walked, not sorted)."""
         total = 0
         for i, r in enumerate(self.rounds_list()):
-            total += r["live"] * ((41 if i == 0 else 52) + 24 * r["passes"])
+            if i == 0:
+                total += r["live"] * (41 + 24 * r["passes"])
+            else:
+                total += r["live"] * 52 + r["sorted"] * 24 * r["passes"]
         return total
 
 

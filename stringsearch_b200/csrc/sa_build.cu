@@ -143,21 +143,101 @@ __global__ void __launch_bounds__(256) k_sample_dups(const KeyGen g, u32 m, u64 
 // chunks), so rank[i] and rank[i + h] are streamed, not gathered.  Output slots come from one
 // atomicAdd per chunk; the order of the sort input does not matter.
 // ------------------------------------------------------------------------------------
+constexpr u32 NO_TAIL = 0xffffffffu;
+constexpr u32 NO_TAIL_IDX = 0xffffffffu;
 constexpr u32 RANK_DEAD = 0x80000000u;
 constexpr u32 RANK_MASK = 0x7fffffffu;
+
+// ---- huge groups ---------------------------------------------------------------------------
+// In repetitive text a few groups hold almost every live suffix, and in each round almost all
+// members of such a group share one sort key (they pair with the same group h symbols on).
+// Sorting them is pointless: they stay one group.  So for a HUGE group (>= HUGE_T slots) one
+// second key half rho* is elected per round (first come); members whose label(i + h) equals it
+// are INERT: they stay in the live list, keep their label, and are neither sorted nor
+// rewritten.  Only the other members are sorted; those below rho* fill the group's slot range
+// from the left, those above from the right, and the range of the inert block shrinks
+// accordingly in the per-group table G[label] = (first slot, last slot).
+// A label that is a multiple of HUGE_M marks a huge group; small groups never use such labels,
+// so a reader knows from the label alone whether the group's state lives in the tables.  What
+// happens to a huge group between rounds (label fell out of the shrunken range, group became
+// small, or unique) is decided once per round by k_huge_prepare and published in STATE; every
+// reader of a huge label resolves it through STATE, members rewrite their own rank on the fly.
+constexpr u32 HUGE_M = 256;
+constexpr u32 HUGE_T = 1u << 16;
+static_assert(HUGE_T >= 2 * HUGE_M, "a huge range must hold two candidate labels");
+constexpr u32 STATE_FINAL = 0x80000000u;
+
+__device__ __forceinline__ bool is_huge_label(u32 lab) { return (lab & (HUGE_M - 1u)) == 0u; }
+
+// Label (1-based slot) for the group occupying slots [s, e], e > s: the middle of the range,
+// moved to a multiple of HUGE_M for huge groups and off such a multiple for small ones.
+// `avoid`: a label that must not be chosen (the label of the huge group this one is split
+// from: its table entry still belongs to the inert block); 0 = none.
+__device__ __forceinline__ u32 pick_label(u32 s, u32 e, u32 avoid) {
+  const u32 mid = s + ((e - s) >> 1) + 1u;
+  if (e - s + 1u >= HUGE_T) {
+    u32 lab = mid & ~(HUGE_M - 1u);
+    if (lab < s + 1u) lab += HUGE_M;
+    if (lab == avoid) lab = (lab + HUGE_M <= e + 1u) ? lab + HUGE_M : lab - HUGE_M;
+    return lab;
+  }
+  if (is_huge_label(mid)) return (mid + 1u <= e + 1u) ? mid + 1u : mid - 1u;
+  return mid;
+}
+
+// rank word -> current label; *fin = the suffix is (or has just become) unique.
+__device__ __forceinline__ u32 resolve_label(u32 w, const u64 *__restrict__ state, u32 round, bool *fin) {
+  *fin = false;
+  if (w & RANK_DEAD) { *fin = true; return w & RANK_MASK; }
+  if (!is_huge_label(w)) return w;
+  const u64 st = __ldg(state + (w / HUGE_M));
+  if ((u32)(st >> 32) != round) return w;  // nothing happened to this group
+  const u32 code = (u32)st;
+  if (code & STATE_FINAL) { *fin = true; return code & RANK_MASK; }
+  return code;  // moved to a new label
+}
+
+// Once per round, one thread per huge group: classify it, publish the verdict in STATE for the
+// readers of this round, and rebuild the list of huge groups.
+__global__ void __launch_bounds__(256) k_huge_prepare(const u32 *__restrict__ hin, u32 cnt, u64 *__restrict__ G,
+                                                      u64 *__restrict__ state, u32 round, u32 *__restrict__ hout,
+                                                      u32 *__restrict__ hout_count) {
+  const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= cnt) return;
+  const u32 lab = hin[j];
+  const u64 g = G[lab];
+  const i64 gs = (i64)(i32)(u32)g, ge = (i64)(i32)(u32)(g >> 32);
+  const i64 size = ge - gs + 1;
+  const u64 tag = (u64)round << 32;
+  if (size <= 0) return;  // every member left the inert block
+  if (size == 1) { state[lab / HUGE_M] = tag | STATE_FINAL | (u32)(gs + 1); return; }
+  if (size < (i64)HUGE_T || !((i64)lab >= gs + 1 && (i64)lab <= ge + 1)) {
+    const u32 nl = pick_label((u32)gs, (u32)ge, 0u);  // small label, or a new huge one inside the range
+    G[nl] = g;
+    state[lab / HUGE_M] = tag | nl;
+    if (is_huge_label(nl)) hout[atomicAdd(hout_count, 1u)] = nl;
+    return;
+  }
+  hout[atomicAdd(hout_count, 1u)] = lab;
+}
 
 struct GatherArgs {
   const u32 *lst_in;  // null: candidates are 0..Lin-1
   u32 Lin;
-  const u32 *rank;
+  u32 *rank;          // read; members of re-labelled / finalised huge groups rewrite their own entry
+  i32 *SA;
   u32 n;
   u64 h;
   u32 lab_bits;
   int npass;
+  u32 round;
+  int filter;         // elect rho* and leave inert members out of the sort
+  const u64 *state;   // [n / HUGE_M + 2] verdicts of k_huge_prepare, tagged with the round
+  u64 *rho;           // [n / HUGE_M + 2] round << 32 | rho*
   u64 *keys_out;
   u32 *vals_out;
   u32 *lst_out;
-  u32 *counter;  // zeroed before launch; ends at the number of live suffixes
+  u32 *counter;       // [0] live suffixes (lst_out), [1] suffixes to sort (keys_out / vals_out); zeroed before launch
   u32 *ghist;
   // sparse mode (few suffixes survived round 0): rank[] holds 0 for every suffix that was
   // already unique after round 0; its label is recomputed on demand from the round-0 order.
@@ -192,8 +272,8 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_gather(const GatherArgs
   constexpr int WARPS = THREADS / 32;
   constexpr u32 CH = THREADS * IPT;
   __shared__ u32 shist[MAX_PASSES * RADIX];
-  __shared__ u32 s_wcnt[WARPS];
-  __shared__ u32 s_base;
+  __shared__ u32 s_wl[WARPS], s_ws[WARPS];
+  __shared__ u32 s_basel, s_bases;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int i = tid; i < a.npass * RADIX; i += THREADS) shist[i] = 0;
   __syncthreads();
@@ -211,43 +291,80 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_gather(const GatherArgs
     }
 #pragma unroll
     for (int k = 0; k < IPT; ++k) {
-      w[k] = (sfx[k] != 0xffffffffu) ? __ldg(a.rank + sfx[k]) : RANK_DEAD;
+      w[k] = (sfx[k] != 0xffffffffu) ? __ldcg(a.rank + sfx[k]) : RANK_DEAD;
       if (w[k] == 0u) w[k] = RANK_DEAD;  // sparse mode: unique since round 0
     }
 #pragma unroll
     for (int k = 0; k < IPT; ++k) {
       const u64 t = (u64)sfx[k] + a.h;
-      r2[k] = (!(w[k] & RANK_DEAD) && t < a.n) ? (__ldg(a.rank + t) & RANK_MASK) : 0u;
+      r2[k] = (!(w[k] & RANK_DEAD) && t < a.n) ? __ldcg(a.rank + t) : 0u;
     }
-
-    u32 off[IPT];  // slot offset inside the warp's output run
-    u32 wtot = 0;
+    // resolve huge labels through this round's verdicts; members fix their own entry
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) {
+      if (!(w[k] & RANK_DEAD)) {
+        bool fin;
+        const u32 lab = resolve_label(w[k], a.state, a.round, &fin);
+        if (fin) {  // its huge group has shrunk to this one suffix
+          a.SA[lab - 1u] = (i32)sfx[k];
+          a.rank[sfx[k]] = RANK_DEAD | lab;
+          w[k] = RANK_DEAD;
+        } else {
+          if (lab != w[k]) a.rank[sfx[k]] = lab;
+          w[k] = lab;
+          if (r2[k] != 0u) r2[k] = resolve_label(r2[k], a.state, a.round, &fin);
+        }
+      }
+    }
+    u32 offl[IPT], offs[IPT];  // slot offsets inside the warp's output runs (live list, sort input)
+    u32 srt = 0;               // bit k: element k goes to the sort
+    u32 wl = 0, ws = 0;
 #pragma unroll
     for (int k = 0; k < IPT; ++k) {
       const bool lv = (w[k] & RANK_DEAD) == 0u;
-      const u64 kx = lv ? (((u64)w[k] << a.lab_bits) | r2[k]) : 0ull;
-      const u32 m = __ballot_sync(0xffffffffu, lv);
-      off[k] = wtot + (u32)__popc(m & lt);
-      wtot += (u32)__popc(m);
-      hist_add(shist, kx, lv, a.npass);
+      bool so = lv;
+      if (lv && a.filter && is_huge_label(w[k])) {
+        // rho* of (group, round): the first member to ask decides
+        u64 *cell = a.rho + (w[k] / HUGE_M);
+        u64 e = ld_volatile_u64(cell);
+        if ((u32)(e >> 32) != a.round) {
+          const u64 want = ((u64)a.round << 32) | r2[k];
+          const u64 old = atomicCAS(reinterpret_cast<unsigned long long *>(cell), (unsigned long long)e, (unsigned long long)want);
+          e = (old == e) ? want : old;
+        }
+        so = (u32)e != r2[k];
+      }
+      const u64 kx = so ? (((u64)w[k] << a.lab_bits) | r2[k]) : 0ull;
+      const u32 ml = __ballot_sync(0xffffffffu, lv), ms = __ballot_sync(0xffffffffu, so);
+      offl[k] = wl + (u32)__popc(ml & lt);
+      offs[k] = ws + (u32)__popc(ms & lt);
+      wl += (u32)__popc(ml);
+      ws += (u32)__popc(ms);
+      srt |= (so ? 1u : 0u) << k;
+      hist_add(shist, kx, so, a.npass);
     }
-    if (lane == 0) s_wcnt[warp] = wtot;
+    if (lane == 0) { s_wl[warp] = wl; s_ws[warp] = ws; }
     __syncthreads();
     if (tid == 0) {
-      u32 tot = 0;
+      u32 tl = 0, ts = 0;
 #pragma unroll
-      for (int x = 0; x < WARPS; ++x) { const u32 c = s_wcnt[x]; s_wcnt[x] = tot; tot += c; }
-      s_base = tot ? atomicAdd(a.counter, tot) : 0u;
+      for (int x = 0; x < WARPS; ++x) {
+        const u32 cl = s_wl[x], cs = s_ws[x];
+        s_wl[x] = tl; s_ws[x] = ts;
+        tl += cl; ts += cs;
+      }
+      s_basel = tl ? atomicAdd(a.counter, tl) : 0u;
+      s_bases = ts ? atomicAdd(a.counter + 1, ts) : 0u;
     }
     __syncthreads();
-    const u32 base = s_base + s_wcnt[warp];
+    const u32 bl = s_basel + s_wl[warp], bs = s_bases + s_ws[warp];
 #pragma unroll
     for (int k = 0; k < IPT; ++k) {
-      if ((w[k] & RANK_DEAD) == 0u) {
-        const u32 o = base + off[k];
+      if ((w[k] & RANK_DEAD) == 0u) a.lst_out[bl + offl[k]] = sfx[k];
+      if ((srt >> k) & 1u) {
+        const u32 o = bs + offs[k];
         a.keys_out[o] = ((u64)w[k] << a.lab_bits) | r2[k];
         a.vals_out[o] = sfx[k];
-        a.lst_out[o] = sfx[k];
         if (a.sa0 != nullptr && r2[k] == 0u && (u64)sfx[k] + a.h < a.n) {
           // sparse mode: suffix i + h has been unique since round 0 and has no stored label;
           // k_lazy_fill computes it (one binary search per entry, all in flight at once)
@@ -257,7 +374,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_gather(const GatherArgs
         }
       }
     }
-    __syncthreads();  // s_wcnt / s_base are reused by the next chunk
+    __syncthreads();  // the shared counters are reused by the next chunk
   }
   for (int i = tid; i < a.npass * RADIX; i += THREADS)
     if (shist[i]) atomicAdd(&a.ghist[i], shist[i]);
@@ -289,6 +406,223 @@ __global__ void __launch_bounds__(THREADS) k_hist_keys(const u64 *__restrict__ k
 }
 
 // ------------------------------------------------------------------------------------
+// Step 2b (after the sort): SA slot of every sorted element.
+// The sorted list holds, group by group (a RUN = maximal stretch with the same label), every
+// live member except the inert ones.  With G[label] = (gs, ge) and, for a huge group, its rho*:
+//   second key half < rho* (or no rho*): slot = gs + (index inside the run)
+//   second key half > rho*             : slot = ge - (elements behind it in the run)
+// Index inside the run needs the run head (forward max-scan, decoupled look-back), elements
+// behind it the run tail (backward min-scan; k_run_summary + k_tail_scan give "first run tail
+// after tile t").  The two ends of the inert block move inwards past the sorted members:
+// the last "<" element and the first ">" element of a run record the new ends in a small
+// update list, applied by k_apply_g after this kernel (G is read here, so it is not written).
+// Bit 31 of the slot word tells the rebuild that the run has an inert block.
+// ------------------------------------------------------------------------------------
+constexpr u64 ST_AGG = 1ull << 62;
+constexpr u64 ST_PRE = 2ull << 62;
+constexpr u64 ST_FLAG = 3ull << 62;
+
+// One 16-byte, 16-byte-aligned access per tile descriptor (a single memory transaction on
+// the hardware).  Both halves carry the state flag, so a torn read -- should one ever
+// happen -- is seen as "flags differ" and simply retried.
+__device__ __forceinline__ ulonglong2 ld_status(const ulonglong2 *p) {
+  ulonglong2 v;
+  asm volatile("ld.volatile.global.v2.u64 {%0,%1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_status(ulonglong2 *p, u64 x, u64 y) {
+  asm volatile("st.volatile.global.v2.u64 [%0], {%1,%2};" ::"l"(p), "l"(x), "l"(y) : "memory");
+}
+
+struct SlotArgs {
+  const u64 *keys;
+  u32 S;
+  u32 lab_bits;
+  const u64 *G;
+  const u64 *rho;
+  u32 round;
+  int filter;
+  u32 *slots;
+  u64 *status;          // [tiles] flag(2) | run head index + 1
+  u32 *tile_rtail;      // [tiles] k_run_summary: first run-tail index inside the tile
+  const u32 *next_rtail;
+  u32 *gupd;            // triples (label, 0 = first slot / 1 = last slot, value)
+  u32 *gupd_count;
+};
+constexpr u32 SLOT_HAS_RHO = 0x80000000u;
+
+template <int THREADS, int IPT>
+__global__ void __launch_bounds__(THREADS) k_run_summary(const SlotArgs a) {
+  constexpr int WARPS = THREADS / 32;
+  __shared__ u32 s_w[WARPS];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const u32 l0 = blockIdx.x * (u32)(THREADS * IPT) + (u32)tid * IPT;
+  u32 v = NO_TAIL_IDX;
+  if (l0 < a.S) {
+    const u32 nvalid = min((u32)IPT, a.S - l0);
+    u32 lab = (u32)(a.keys[l0] >> a.lab_bits);
+    for (u32 j = 0; j < nvalid; ++j) {
+      const u32 l = l0 + j;
+      const bool last = l + 1 >= a.S;
+      const u32 nlab = last ? 0u : (u32)(a.keys[l + 1] >> a.lab_bits);
+      if (last || nlab != lab) { v = l; break; }
+      lab = nlab;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+  if (lane == 0) s_w[warp] = v;
+  __syncthreads();
+  if (tid == 0) {
+    u32 m = NO_TAIL_IDX;
+#pragma unroll
+    for (int w = 0; w < WARPS; ++w) m = min(m, s_w[w]);
+    a.tile_rtail[blockIdx.x] = m;
+  }
+}
+
+template <int THREADS, int IPT>
+__global__ void __launch_bounds__(THREADS, 2) k_slots(const SlotArgs a) {
+  constexpr int WARPS = THREADS / 32;
+  constexpr int TILE = THREADS * IPT;
+  __shared__ u32 s_wh[WARPS], s_wt[WARPS];
+  __shared__ u32 s_pre;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const u32 tile = blockIdx.x;
+  const u32 S = a.S;
+  const u32 l0 = tile * (u32)TILE + (u32)tid * IPT;
+  u32 nvalid = 0;
+  if (l0 < S) nvalid = min((u32)IPT, S - l0);
+  // labels (first key half) of the IPT elements and of one neighbour on each side; second halves
+  u32 lab[IPT + 2], r2[IPT + 2];
+  const u64 r2mask = (1ull << a.lab_bits) - 1ull;
+#pragma unroll
+  for (int j = 0; j < IPT + 2; ++j) {
+    const i64 l = (i64)l0 + j - 1;
+    u64 kx = 0;
+    if (l >= 0 && l < (i64)S && (j == 0 ? nvalid > 0 : (u32)(j - 1) <= nvalid)) kx = a.keys[l];
+    lab[j] = (u32)(kx >> a.lab_bits);
+    r2[j] = (u32)(kx & r2mask);
+  }
+  // run flags: bit j = element l0+j starts a run (beyond-the-end counts as a start)
+  u32 f = 0;
+#pragma unroll
+  for (int j = 0; j <= IPT; ++j) {
+    const u32 l = l0 + j;
+    f |= ((l == 0 || l >= S || lab[j + 1] != lab[j]) ? 1u : 0u) << j;
+  }
+  u32 th = 0, tt = NO_TAIL_IDX;  // last run head index + 1, first run tail index
+#pragma unroll
+  for (int j = 0; j < IPT; ++j)
+    if ((u32)j < nvalid && ((f >> j) & 1u)) th = l0 + j + 1u;
+#pragma unroll
+  for (int j = IPT - 1; j >= 0; --j)
+    if ((u32)j < nvalid && ((f >> (j + 1)) & 1u)) tt = l0 + j;
+  u32 ih = th, it = tt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const u32 yh = __shfl_up_sync(0xffffffffu, ih, o);
+    const u32 yt = __shfl_down_sync(0xffffffffu, it, o);
+    if (lane >= o) ih = max(ih, yh);
+    if (lane + o < 32) it = min(it, yt);
+  }
+  if (lane == 31) s_wh[warp] = ih;
+  if (lane == 0) s_wt[warp] = it;
+  u32 eh = __shfl_up_sync(0xffffffffu, ih, 1);
+  u32 et = __shfl_down_sync(0xffffffffu, it, 1);
+  if (lane == 0) eh = 0;
+  if (lane == 31) et = NO_TAIL_IDX;
+  __syncthreads();
+  u32 bh = 0;
+#pragma unroll
+  for (int w = 0; w < WARPS; ++w) {
+    if (w < warp) eh = max(eh, s_wh[w]);
+    if (w > warp) et = min(et, s_wt[w]);
+    bh = max(bh, s_wh[w]);
+  }
+  et = min(et, a.next_rtail[tile]);
+  // tile prefix: run head index + 1 of the last run start before this tile (decoupled look-back)
+  if (warp == 0) {
+    u32 xh = 0;
+    if (tile == 0) {
+      if (lane == 0) st_volatile_u64(a.status, ST_PRE | bh);
+    } else {
+      if (lane == 0) st_volatile_u64(a.status + tile, ST_AGG | bh);
+      i64 look = (i64)tile - 1 - lane;
+      for (;;) {
+        u64 sv = ST_PRE;
+        if (look >= 0) {
+          do { sv = ld_volatile_u64(a.status + look); } while ((sv & ST_FLAG) == 0);
+        }
+        const u32 pre = __ballot_sync(0xffffffffu, (sv & ST_FLAG) == ST_PRE);
+        const int first = pre ? (__ffs(pre) - 1) : 32;
+        u32 vh = (lane <= first) ? (u32)(sv & 0xffffffffull) : 0u;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) vh = max(vh, __shfl_xor_sync(0xffffffffu, vh, o));
+        xh = max(xh, vh);
+        if (pre) break;
+        look -= 32;
+      }
+      if (lane == 0) st_volatile_u64(a.status + tile, ST_PRE | max(xh, bh));
+    }
+    if (lane == 0) s_pre = xh;
+  }
+  __syncthreads();
+  u32 rt[IPT];  // run tail index of every element
+  {
+    u32 cur = et;
+#pragma unroll
+    for (int j = IPT - 1; j >= 0; --j) {
+      if ((u32)j < nvalid && ((f >> (j + 1)) & 1u)) cur = l0 + j;
+      rt[j] = cur;
+    }
+  }
+  u32 rh = max(s_pre, eh);  // run head index + 1
+  u32 gs = 0, ge = 0, rho = 0;
+  bool has_rho = false;
+#pragma unroll
+  for (int j = 0; j < IPT; ++j) {
+    if ((u32)j < nvalid) {
+      const u32 l = l0 + j;
+      const bool start = (f >> j) & 1u;
+      if (start) rh = l + 1u;
+      if (start || j == 0) {  // (re)load the group's table entry
+        const u32 lb = lab[j + 1];
+        const u64 g = __ldcg(a.G + lb);
+        gs = (u32)g; ge = (u32)(g >> 32);
+        has_rho = false;
+        if (a.filter && is_huge_label(lb)) {
+          const u64 e = __ldcg(a.rho + (lb / HUGE_M));
+          if ((u32)(e >> 32) == a.round) { has_rho = true; rho = (u32)e; }
+        }
+      }
+      const u32 A = l - (rh - 1u), B = rt[j] - l;
+      const bool less = !has_rho || r2[j + 1] < rho;
+      const u32 slot = less ? (gs + A) : (ge - B);
+      a.slots[l] = slot | (has_rho ? SLOT_HAS_RHO : 0u);
+      if (has_rho) {
+        const bool is_tail = (f >> (j + 1)) & 1u;
+        if (less && (is_tail || !(r2[j + 2] < rho))) {   // last element left of the inert block
+          const u32 q = atomicAdd(a.gupd_count, 1u);
+          a.gupd[3 * q] = lab[j + 1]; a.gupd[3 * q + 1] = 0u; a.gupd[3 * q + 2] = slot + 1u;
+        }
+        if (!less && (start || r2[j] < rho)) {           // first element right of it
+          const u32 q = atomicAdd(a.gupd_count, 1u);
+          a.gupd[3 * q] = lab[j + 1]; a.gupd[3 * q + 1] = 1u; a.gupd[3 * q + 2] = slot - 1u;
+        }
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_apply_g(const u32 *__restrict__ gupd, const u32 *__restrict__ count, u64 *__restrict__ G) {
+  const u32 q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= *count) return;
+  u32 *half = reinterpret_cast<u32 *>(G + gupd[3 * q]);
+  half[gupd[3 * q + 1]] = gupd[3 * q + 2];
+}
+
+// ------------------------------------------------------------------------------------
 // Step 3 (after the sort): re-flag, re-label, finalise, compact.  Sorted live elements l
 // (key[l], suffix[l]) sit in SA slots pos[l] (ascending).  With
 //   flag[l] = key[l] != key[l-1]           (round 0: also around short suffixes)
@@ -308,36 +642,21 @@ __global__ void __launch_bounds__(THREADS) k_hist_keys(const u64 *__restrict__ k
 struct RebuildArgs {
   const u64 *keys;
   const u32 *sufx;
-  const u32 *pos_in;   // null in round 0 (slot == index)
+  const u32 *pos_in;   // k_slots output (bit 31: the run has an inert block); null in round 0 (slot == index)
   u32 L;
   u32 short_from;      // round 0: suffix indices >= short_from are short (forced singletons)
   u32 lab_bits;        // old label = key >> lab_bits (rounds >= 1)
   u32 *rank;
   i32 *SA;
-  u32 *pos_out;
+  u64 *G;              // [n + 2] slot range of every live group, indexed by its label
+  u32 *hlist;          // labels of the huge groups created in this round are appended here
+  u32 *hcount;
   ulonglong2 *status;  // [tiles] x = flag(2) | head+1 ; y = flag(2) | survivors(31) | groups(31)
   u32 *survivors;      // [1] k_tail_summary: number of elements that stay live after this round
   u32 *tile_tail;      // [tiles] k_tail_summary: first tail slot inside the tile (or NO_TAIL)
   const u32 *next_tail;  // [tiles] k_tail_scan: first tail slot in any later tile
   RoundResult *result;
 };
-
-constexpr u32 NO_TAIL = 0xffffffffu;
-constexpr u64 ST_AGG = 1ull << 62;
-constexpr u64 ST_PRE = 2ull << 62;
-constexpr u64 ST_FLAG = 3ull << 62;
-
-// One 16-byte, 16-byte-aligned access per tile descriptor (a single memory transaction on
-// the hardware).  Both halves carry the state flag, so a torn read -- should one ever
-// happen -- is seen as "flags differ" and simply retried.
-__device__ __forceinline__ ulonglong2 ld_status(const ulonglong2 *p) {
-  ulonglong2 v;
-  asm volatile("ld.volatile.global.v2.u64 {%0,%1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_status(ulonglong2 *p, u64 x, u64 y) {
-  asm volatile("st.volatile.global.v2.u64 [%0], {%1,%2};" ::"l"(p), "l"(x), "l"(y) : "memory");
-}
 
 // Loads the IPT consecutive elements of this thread plus one neighbour on each side and
 // returns the flag bits f (bit j = flag of element l0 + j, j = 0..IPT; beyond-the-end counts
@@ -400,7 +719,7 @@ __global__ void __launch_bounds__(THREADS) k_tail_summary(const RebuildArgs a) {
     const u32 tails = (f >> 1) & vm;  // element j is a tail iff element j+1 is flagged
     if (tails) {
       const u32 l = l0 + (u32)(__ffs(tails) - 1);
-      v = ROUND0 ? l : a.pos_in[l];
+      v = ROUND0 ? l : (a.pos_in[l] & ~SLOT_HAS_RHO);
     }
     surv = (u32)__popc(~(f & (f >> 1)) & vm);  // not (head and tail) = not unique yet
   }
@@ -485,6 +804,14 @@ __global__ void __launch_bounds__(THREADS, 2) k_rebuild(const RebuildArgs a) {
   } else {
 #pragma unroll
     for (int j = 0; j < IPT; ++j) px[j] = (l0 + j < L) ? a.pos_in[l0 + j] : 0;
+  }
+  u32 hr = 0;  // bit j: element j belongs to a run with an inert block (its old label stays with that block)
+  if (!ROUND0) {
+#pragma unroll
+    for (int j = 0; j < IPT; ++j) {
+      hr |= (px[j] >> 31) << j;
+      px[j] &= ~SLOT_HAS_RHO;
+    }
   }
   u32 nvalid = 0;
   if (l0 < L) nvalid = min((u32)IPT, L - l0);
@@ -600,9 +927,16 @@ __global__ void __launch_bounds__(THREADS, 2) k_rebuild(const RebuildArgs a) {
         if (MODE == RB_NORMAL) a.rank[sx[j + 1]] = RANK_DEAD | s1;
       } else {
         const u32 old = ROUND0 ? 0u : (u32)(kx[j + 1] >> a.lab_bits);
-        if (old < s1 || old > e1) a.rank[sx[j + 1]] = s1 + ((e1 - s1) >> 1);
+        const bool inert_owner = (hr >> j) & 1u;  // the old label stays with the run's inert block
+        const bool keep = !ROUND0 && !inert_owner && old >= s1 && old <= e1;
+        const u32 lab = keep ? old : pick_label(s1 - 1u, e1 - 1u, inert_owner ? old : 0u);
+        if (!keep) a.rank[sx[j + 1]] = lab;
+        if ((f >> j) & 1u) {  // group head: publish the group's slot range
+          a.G[lab] = (u64)(s1 - 1u) | ((u64)(e1 - 1u) << 32);
+          if (!keep && is_huge_label(lab)) a.hlist[atomicAdd(a.hcount, 1u)] = lab;
+        }
         if (MODE == RB_SPARSE) a.SA[px[j]] = (i32)sx[j + 1];
-        a.pos_out[c++] = px[j];
+        ++c;
       }
     }
   }
@@ -637,7 +971,13 @@ struct Carve {
 
 struct Layout {
   u64 *packed; u64 packed_words;
-  u64 *keys[2]; u32 *vals[2]; u32 *pos[2]; u32 *lst[2]; u32 *rank;
+  u64 *keys[2]; u32 *vals[2]; u32 *slots; u32 *lst[2]; u32 *rank;
+  u64 *G;                      // [n + 2] slot range of every live group, indexed by label
+  u64 *state, *rho;            // [n / HUGE_M + 2] per huge label
+  u32 *hlist[2]; u32 hcap;     // labels of the huge groups
+  u32 *hcount;                 // [2]
+  u32 *gupd; u32 *gupd_count;  // end-of-inert-block updates of one round
+  u64 *slot_status; u32 *tile_rtail, *next_rtail;
   u32 *ghist;      // [MAX_PASSES][256]
   u32 *bin_base;   // [MAX_PASSES][256]
   u32 *present;    // [256]
@@ -659,7 +999,15 @@ Layout make_layout(char *base, u32 n) {
   y.packed = c.take<u64>(y.packed_words);
   y.keys[0] = c.take<u64>(N); y.keys[1] = c.take<u64>(N);
   y.vals[0] = c.take<u32>(N); y.vals[1] = c.take<u32>(N);
-  y.pos[0] = c.take<u32>(N);  y.pos[1] = c.take<u32>(N);
+  y.slots = c.take<u32>(N);
+  y.G = c.take<u64>(N + 2);
+  y.state = c.take<u64>(N / HUGE_M + 2);
+  y.rho = c.take<u64>(N / HUGE_M + 2);
+  y.hcap = (u32)(2 * (N / HUGE_T) + 4096);
+  y.hlist[0] = c.take<u32>(y.hcap); y.hlist[1] = c.take<u32>(y.hcap);
+  y.hcount = c.take<u32>(64);
+  y.gupd = c.take<u32>(3 * (size_t)y.hcap);
+  y.gupd_count = c.take<u32>(64);
   y.lst[0] = c.take<u32>(N);  y.lst[1] = c.take<u32>(N);
   y.rank = c.take<u32>(N);
   y.ghist = c.take<u32>(MAX_PASSES * RADIX);
@@ -676,6 +1024,9 @@ Layout make_layout(char *base, u32 n) {
   y.rb_status = c.take<ulonglong2>(rtiles + 1);
   y.tile_tail = c.take<u32>(rtiles + 1);
   y.next_tail = c.take<u32>(rtiles + 1);
+  y.slot_status = c.take<u64>(rtiles + 1);
+  y.tile_rtail = c.take<u32>(rtiles + 1);
+  y.next_rtail = c.take<u32>(rtiles + 1);
   y.total = c.used;
   return y;
 }
@@ -851,7 +1202,7 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
     // ... unless the text is repetitive: then nearly everything survives round 0 whatever its
     // depth, and a deeper start means fewer doubling rounds.
     constexpr u32 M = 1u << 16, TBL = 1u << 18;
-    u64 *table = reinterpret_cast<u64 *>(y.pos[0]);
+    u64 *table = reinterpret_cast<u64 *>(y.slots);
     GSA_TRY(cudaMemsetAsync(table, 0, TBL * sizeof(u64), st));
     GSA_TRY(cudaMemsetAsync(y.survivors, 0, sizeof(u32), st));
     KeyGen probe{y.packed, n, 0, b, k_want * b};
@@ -889,20 +1240,24 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
 
   const u32 lab_bits = bits_for(n);  // labels are 1..n
   bool sparse = false;
+  int hcur = 0;  // hlist[hcur] / hcount[hcur]: huge groups entering the next round
+  GSA_TRY(cudaMemsetAsync(y.state, 0, ((size_t)n / HUGE_M + 2) * sizeof(u64), st));
+  GSA_TRY(cudaMemsetAsync(y.rho, 0, ((size_t)n / HUGE_M + 2) * sizeof(u64), st));
+  GSA_TRY(cudaMemsetAsync(y.hcount, 0, 2 * sizeof(u32), st));
   // tail summaries + survivor count, then the rebuild proper.  *survivors_out is known before the
   // rebuild is launched, which lets the last round skip its rank writes.
-  auto launch_rebuild = [&](bool round0, u32 L, int kv, int pin, int pout, u32 *survivors_out) -> int {
+  auto launch_rebuild = [&](bool round0, u32 L, int kv, bool may_finish, u32 *survivors_out) -> int {
     const u32 tiles = (u32)div_up(L, RB_TILE);
     GSA_TRY(cudaMemsetAsync(y.rb_status, 0, (size_t)tiles * sizeof(ulonglong2), st));
     GSA_TRY(cudaMemsetAsync(y.survivors, 0, sizeof(u32), st));
     RebuildArgs r;
     r.keys = y.keys[kv]; r.sufx = y.vals[kv];
-    r.pos_in = round0 ? nullptr : y.pos[pin];
+    r.pos_in = round0 ? nullptr : y.slots;
     r.L = L;
     r.short_from = round0 ? (n - ns) : 0xffffffffu;
     r.lab_bits = lab_bits;
     r.rank = y.rank; r.SA = d_SA;
-    r.pos_out = y.pos[pout];
+    r.G = y.G; r.hlist = y.hlist[hcur]; r.hcount = y.hcount + hcur;
     r.status = y.rb_status;
     r.survivors = y.survivors;
     r.tile_tail = y.tile_tail; r.next_tail = y.next_tail;
@@ -916,15 +1271,16 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
     GSA_TRY(cudaMemcpyAsync(&surv, y.survivors, sizeof(u32), cudaMemcpyDeviceToHost, st));
     GSA_TRY(cudaStreamSynchronize(st));
     *survivors_out = surv;
+    const bool fin = may_finish && surv == 0;  // nothing is live after this round
     if (round0) {
       // few survivors: do not scatter n ranks for the sake of a handful of look-ups
       sparse = surv != 0 && (u64)surv * 64 < n && !getenv("GSA_NO_SPARSE");
       if (sparse) GSA_TRY(cudaMemsetAsync(y.rank, 0, (size_t)n * sizeof(u32), st));
-      if (surv == 0) k_rebuild<RB_THREADS, RB_IPT, true, RB_FINAL><<<tiles, RB_THREADS, 0, st>>>(r);
+      if (fin) k_rebuild<RB_THREADS, RB_IPT, true, RB_FINAL><<<tiles, RB_THREADS, 0, st>>>(r);
       else if (sparse) k_rebuild<RB_THREADS, RB_IPT, true, RB_SPARSE><<<tiles, RB_THREADS, 0, st>>>(r);
       else k_rebuild<RB_THREADS, RB_IPT, true, RB_NORMAL><<<tiles, RB_THREADS, 0, st>>>(r);
     } else {
-      if (surv == 0) k_rebuild<RB_THREADS, RB_IPT, false, RB_FINAL><<<tiles, RB_THREADS, 0, st>>>(r);
+      if (fin) k_rebuild<RB_THREADS, RB_IPT, false, RB_FINAL><<<tiles, RB_THREADS, 0, st>>>(r);
       else k_rebuild<RB_THREADS, RB_IPT, false, RB_NORMAL><<<tiles, RB_THREADS, 0, st>>>(r);
     }
     KLAUNCH_CHECK();
@@ -932,76 +1288,116 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
     return GSA_OK;
   };
 
-  RoundResult rr{};
   u32 survivors = 0;
-  GSA_TRY_RC(launch_rebuild(true, n, cur, 0, 0, &survivors));
-  GSA_TRY(cudaMemcpyAsync(&rr, y.result, sizeof(rr), cudaMemcpyDeviceToHost, st));
+  GSA_TRY_RC(launch_rebuild(true, n, cur, true, &survivors));
   GSA_TRY(cudaEventRecord(ev[3], st));
   GSA_TRY(cudaStreamSynchronize(st));
   u32 round = 0;
-  auto log_round = [&](u64 depth, u64 live, u32 groups, u32 kb, u32 np) {
+  auto log_round = [&](u64 depth, u64 live, u32 sorted, u32 groups, u32 kb, u32 np) {
     const float pass_ms = timer.drain();
     if (!stats) return;
     stats->ms_radix_passes += pass_ms;
     if (round >= GSA_MAX_ROUNDS) return;
     gsa_round_stat &s = stats->round[round];
-    s.depth = depth; s.live = live; s.groups = groups; s.key_bits = kb; s.passes = np;
+    s.depth = depth; s.live = live; s.sorted = sorted; s.groups = groups; s.key_bits = kb; s.passes = np;
     cudaEventElapsedTime(&s.ms_total, ev[0], ev[3]);
     cudaEventElapsedTime(&s.ms_sort, ev[1], ev[2]);
     stats->rounds = round + 1;
   };
-  log_round(k, n, 0, key_bits, passes);
+  log_round(k, n, n, 0, key_bits, passes);
 
   // ---- doubling rounds ------------------------------------------------------------------------
-  int pcur = 0;        // pos buffer holding the slots of the live elements (SA order)
   int lcur = 0;        // lst buffer holding the candidates (text order); round 1 uses 0..n-1
-  u32 Lcand = n;
+  u32 Lcand = n;       // candidates to walk
+  u32 live = survivors;
   bool ident = true;
   u64 h = k;           // suffixes are sorted by their first h symbols
   const u32 kb = 2 * lab_bits;
   const int npass = (int)div_up(kb, 8);
-  while (rr.live_out > 0) {
+  const bool filter_allowed = !getenv("GSA_NO_INERT");
+  while (live > 0) {
     ++round;
-    const u32 L = rr.live_out, G = rr.groups_out;
     GSA_TRY(cudaEventRecord(ev[0], st));
+    // huge groups: verdicts for this round, and the list for the next one
+    u32 hc = 0;
+    GSA_TRY(cudaMemcpyAsync(&hc, y.hcount + hcur, sizeof(u32), cudaMemcpyDeviceToHost, st));
+    GSA_TRY(cudaStreamSynchronize(st));
+    if (hc > y.hcap / 2) { set_error("huge-group list overflow", __FILE__, __LINE__); return GSA_ECUDA; }
+    GSA_TRY(cudaMemsetAsync(y.hcount + (hcur ^ 1), 0, sizeof(u32), st));
+    if (hc) {
+      k_huge_prepare<<<(u32)div_up(hc, 256), 256, 0, st>>>(y.hlist[hcur], hc, y.G, y.state, round, y.hlist[hcur ^ 1], y.hcount + (hcur ^ 1));
+      KLAUNCH_CHECK();
+      if (stats) stats->kernel_launches++;
+    }
+    hcur ^= 1;  // the rebuild of this round appends the huge groups it creates to the new list
+    const bool filter = filter_allowed && !sparse && hc > 0;
     GSA_TRY(cudaMemsetAsync(y.ghist, 0, MAX_PASSES * RADIX * sizeof(u32), st));
-    GSA_TRY(cudaMemsetAsync(y.live_counter, 0, sizeof(u32), st));
+    GSA_TRY(cudaMemsetAsync(y.live_counter, 0, 2 * sizeof(u32), st));
     GatherArgs g;
     g.lst_in = ident ? nullptr : y.lst[lcur];
-    g.Lin = Lcand; g.rank = y.rank; g.n = n; g.h = h; g.lab_bits = lab_bits;
+    g.Lin = Lcand; g.rank = y.rank; g.SA = d_SA; g.n = n; g.h = h; g.lab_bits = lab_bits;
     g.npass = sparse ? 0 : npass;  // sparse: keys are completed by k_lazy_fill, histogram afterwards
+    g.round = round; g.filter = filter ? 1 : 0; g.state = y.state; g.rho = y.rho;
     g.keys_out = y.keys[0]; g.vals_out = y.vals[0]; g.lst_out = y.lst[lcur ^ 1];
     g.counter = y.live_counter; g.ghist = y.ghist;
     g.sa0 = sparse ? d_SA : nullptr;
     g.gen = gen;
-    g.todo = y.pos[pcur ^ 1];  // free until this round's rebuild writes it
+    g.todo = y.slots;  // free until k_slots of this round
     g.todo_count = y.survivors;
     if (sparse) GSA_TRY(cudaMemsetAsync(y.survivors, 0, sizeof(u32), st));
     const u32 gblocks = (u32)std::min<u64>((u64)sms * GA_BLOCKS_PER_SM, std::max<u64>(1, div_up(Lcand, GA_THREADS * GA_IPT)));
     k_gather<GA_THREADS, GA_IPT, GA_BLOCKS_PER_SM><<<gblocks, GA_THREADS, 0, st>>>(g);
     KLAUNCH_CHECK();
     if (stats) stats->kernel_launches++;
-    if (sparse) {
-      // at most one entry per live suffix (L of them; L * 64 < n, so the pairs fit in one pos buffer)
-      k_lazy_fill<<<(u32)div_up(L, 256), 256, 0, st>>>(gen, d_SA, g.todo, g.todo_count, y.keys[0]);
-      KLAUNCH_CHECK();
-      const u32 hb = (u32)std::min<u64>((u64)sms * 4, std::max<u64>(1, div_up(L, HIST_THREADS)));
-      k_hist_keys<HIST_THREADS><<<hb, HIST_THREADS, 0, st>>>(y.keys[0], L, npass, y.ghist);
-      KLAUNCH_CHECK();
-      if (stats) stats->kernel_launches += 2;
-    }
+    u32 cnt[2] = {0, 0};  // live suffixes found, of which to sort
+    GSA_TRY(cudaMemcpyAsync(cnt, y.live_counter, sizeof(cnt), cudaMemcpyDeviceToHost, st));
+    GSA_TRY(cudaStreamSynchronize(st));
+    const u32 Llive = cnt[0], S = cnt[1];
+    passes = 0;
+    survivors = 0;
     GSA_TRY(cudaEventRecord(ev[1], st));
-    GSA_TRY_RC(run_passes(y, L, npass, 0, nullptr, st, stats, timer, &cur, &passes));
     GSA_TRY(cudaEventRecord(ev[2], st));
-    GSA_TRY_RC(launch_rebuild(false, L, cur, pcur, pcur ^ 1, &survivors));
-    GSA_TRY(cudaMemcpyAsync(&rr, y.result, sizeof(rr), cudaMemcpyDeviceToHost, st));
+    if (S > 0) {
+      if (sparse) {
+        // at most one entry per sorted suffix (S * 64 < n, so the pairs fit in the slot buffer)
+        k_lazy_fill<<<(u32)div_up(S, 256), 256, 0, st>>>(gen, d_SA, g.todo, g.todo_count, y.keys[0]);
+        KLAUNCH_CHECK();
+        const u32 hb = (u32)std::min<u64>((u64)sms * 4, std::max<u64>(1, div_up(S, HIST_THREADS)));
+        k_hist_keys<HIST_THREADS><<<hb, HIST_THREADS, 0, st>>>(y.keys[0], S, npass, y.ghist);
+        KLAUNCH_CHECK();
+        if (stats) stats->kernel_launches += 2;
+      }
+      GSA_TRY(cudaEventRecord(ev[1], st));
+      GSA_TRY_RC(run_passes(y, S, npass, 0, nullptr, st, stats, timer, &cur, &passes));
+      GSA_TRY(cudaEventRecord(ev[2], st));
+      // SA slots of the sorted elements from the group tables
+      const u32 tiles = (u32)div_up(S, RB_TILE);
+      SlotArgs sa;
+      sa.keys = y.keys[cur]; sa.S = S; sa.lab_bits = lab_bits; sa.G = y.G; sa.rho = y.rho; sa.round = round;
+      sa.filter = filter ? 1 : 0; sa.slots = y.slots; sa.status = y.slot_status;
+      sa.tile_rtail = y.tile_rtail; sa.next_rtail = y.next_rtail; sa.gupd = y.gupd; sa.gupd_count = y.gupd_count;
+      GSA_TRY(cudaMemsetAsync(y.slot_status, 0, (size_t)tiles * sizeof(u64), st));
+      GSA_TRY(cudaMemsetAsync(y.gupd_count, 0, sizeof(u32), st));
+      k_run_summary<RB_THREADS, RB_IPT><<<tiles, RB_THREADS, 0, st>>>(sa);
+      KLAUNCH_CHECK();
+      k_tail_scan<<<1, 1024, 0, st>>>(y.tile_rtail, y.next_rtail, tiles);
+      KLAUNCH_CHECK();
+      k_slots<RB_THREADS, RB_IPT><<<tiles, RB_THREADS, 0, st>>>(sa);
+      KLAUNCH_CHECK();
+      if (filter) {
+        k_apply_g<<<(u32)div_up(2 * (u64)hc + 2, 256), 256, 0, st>>>(y.gupd, y.gupd_count, y.G);
+        KLAUNCH_CHECK();
+      }
+      if (stats) stats->kernel_launches += 4;
+      GSA_TRY_RC(launch_rebuild(false, S, cur, Llive == S, &survivors));
+    }
     GSA_TRY(cudaEventRecord(ev[3], st));
     GSA_TRY(cudaStreamSynchronize(st));
     h *= 2;
-    log_round(h, L, G, kb, passes);
-    pcur ^= 1;
+    log_round(h, Llive, S, hc, kb, passes);
+    live = (Llive - S) + survivors;  // inert members + non-unique sorted ones
     lcur ^= 1;
-    Lcand = L;
+    Lcand = Llive;
     ident = false;
     if (round > 64) { set_error("prefix doubling did not converge", __FILE__, __LINE__); return GSA_ECUDA; }
   }

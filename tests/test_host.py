@@ -102,6 +102,30 @@ def test_design_model_matches_oracle(port, sa_golden):
         assert (build_sa_model(t, sparse=True, key_symbols=2) == port.sa_build(t)).all()
 
 
+def test_v4_model_matches_oracle(port, sa_golden):
+    """tests/model_v4.py: inert-majority filter for huge groups + table-based slot ranges (the
+    scheme of sa_build.cu's doubling rounds), with tiny thresholds so that small inputs use it."""
+    from model_v4 import build_sa_v4
+
+    for name, text, sa in sa_golden:
+        if len(text) <= 1200:
+            assert build_sa_v4(text, M=4, T=8).tolist() == sa.tolist(), name
+    rng = np.random.default_rng(4)
+    cases = [b"a" * 300, b"ab" * 200 + b"b" + b"ab" * 100, b"abc" * 150]
+    for per, nn, mut in ((50, 2500, 20), (7, 2000, 8), (13, 1500, 0)):
+        base = rng.integers(0, 256, per, dtype=np.uint8)
+        x = np.tile(base, nn // per + 1)[:nn].copy()
+        idx = rng.integers(0, nn, mut)
+        x[idx] = rng.integers(0, 256, mut)
+        cases.append(x.tobytes())
+    for i, t in enumerate(cases):
+        exp = port.sa_build(t)
+        for (M, T) in ((4, 8), (2, 4), (8, 32)):
+            st = []
+            assert (build_sa_v4(t, M=M, T=T, shuffle_seed=i, stats=st) == exp).all(), (i, M, T)
+        assert any(inert > 0 for (_, _, _, inert) in st)  # the filter really was exercised
+
+
 def test_synth_shapes():
     from stringsearch_b200 import synth
 

@@ -15,5 +15,5 @@ for path in sys.argv[1:]:
           f"whole-build frac {rf.get('whole_build', {}).get('frac_of_peak', 0):.3f}  cpu {d.get('cpu_baseline', {}).get('value')}")
     if "-v" in sys.argv or len(d.get("rounds", [])) > 1:
         for r in d.get("rounds", []):
-            print(f"    h={r['depth']:<6} L={r['live']:<11} G={r['groups']:<10} bits={r['key_bits']} p={r['passes']} "
+            print(f"    h={r['depth']:<6} L={r['live']:<11} S={r.get('sorted', r['live']):<11} hugeG={r['groups']:<8} bits={r['key_bits']} p={r['passes']} "
                   f"ms={r['ms_total']:.2f} sort={r['ms_sort']:.2f}")
