@@ -152,9 +152,11 @@ constexpr u32 RANK_MASK = 0x7fffffffu;
 // In repetitive text a few groups hold almost every live suffix, and in each round almost all
 // members of such a group share one sort key (they pair with the same group h symbols on).
 // Sorting them is pointless: they stay one group.  So for a HUGE group (>= HUGE_T slots) one
-// second key half rho* is elected per round (first come); members whose label(i + h) equals it
-// are INERT: they stay in the live list, keep their label, and are neither sorted nor
-// rewritten.  Only the other members are sorted; those below rho* fill the group's slot range
+// second key half rho* is chosen per round -- the one of a representative member, which is
+// refreshed from the members that were inert in the previous round (they are exactly the
+// members of the group now) -- and members whose label(i + h) equals it are INERT: they stay
+// in the live list, keep their label, and are neither sorted nor rewritten.  Any choice of
+// rho* is correct; a bad one only means a round in which the group is sorted in full.  Only the other members are sorted; those below rho* fill the group's slot range
 // from the left, those above from the right, and the range of the inert block shrinks
 // accordingly in the per-group table G[label] = (first slot, last slot).
 // A label that is a multiple of HUGE_M marks a huge group; small groups never use such labels,
@@ -200,8 +202,8 @@ __device__ __forceinline__ u32 resolve_label(u32 w, const u64 *__restrict__ stat
 // Once per round, one thread per huge group: classify it, publish the verdict in STATE for the
 // readers of this round, and rebuild the list of huge groups.
 __global__ void __launch_bounds__(256) k_huge_prepare(const u32 *__restrict__ hin, u32 cnt, u64 *__restrict__ G,
-                                                      u64 *__restrict__ state, u32 round, u32 *__restrict__ hout,
-                                                      u32 *__restrict__ hout_count) {
+                                                      u64 *__restrict__ state, u32 *__restrict__ rep, u32 round,
+                                                      u32 *__restrict__ hout, u32 *__restrict__ hout_count) {
   const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= cnt) return;
   const u32 lab = hin[j];
@@ -215,10 +217,37 @@ __global__ void __launch_bounds__(256) k_huge_prepare(const u32 *__restrict__ hi
     const u32 nl = pick_label((u32)gs, (u32)ge, 0u);  // small label, or a new huge one inside the range
     G[nl] = g;
     state[lab / HUGE_M] = tag | nl;
-    if (is_huge_label(nl)) hout[atomicAdd(hout_count, 1u)] = nl;
+    if (is_huge_label(nl)) {
+      rep[nl / HUGE_M] = rep[lab / HUGE_M];
+      hout[atomicAdd(hout_count, 1u)] = nl;
+    }
     return;
   }
   hout[atomicAdd(hout_count, 1u)] = lab;
+}
+
+// After the verdicts: rho* of every huge group for this round = label(rep + h), provided the
+// representative still belongs to the group (otherwise the group goes unfiltered this round).
+__global__ void __launch_bounds__(256) k_huge_rho(const u32 *__restrict__ hl, const u32 *__restrict__ hl_count,
+                                                  const u32 *__restrict__ rank, const u64 *__restrict__ state,
+                                                  const u32 *__restrict__ rep, u64 *__restrict__ rho, u32 round, u64 h,
+                                                  u32 n) {
+  const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= *hl_count) return;
+  const u32 lab = hl[j];
+  const u32 r = rep[lab / HUGE_M];
+  if (r >= n) return;
+  bool fin;
+  const u32 w = rank[r];
+  if (w == 0u || resolve_label(w, state, round, &fin) != lab || fin) return;
+  const u64 t = (u64)r + h;
+  u32 r2 = 0;
+  if (t < n) {
+    const u32 w2 = rank[t];
+    if (w2 == 0u) return;  // sparse mode keeps no label for it
+    r2 = resolve_label(w2, state, round, &fin);
+  }
+  rho[lab / HUGE_M] = ((u64)round << 32) | r2;
 }
 
 struct GatherArgs {
@@ -233,7 +262,8 @@ struct GatherArgs {
   u32 round;
   int filter;         // elect rho* and leave inert members out of the sort
   const u64 *state;   // [n / HUGE_M + 2] verdicts of k_huge_prepare, tagged with the round
-  u64 *rho;           // [n / HUGE_M + 2] round << 32 | rho*
+  const u64 *rho;     // [n / HUGE_M + 2] round << 32 | rho*  (k_huge_rho)
+  u32 *rep;           // [n / HUGE_M + 2] a member of every huge group, refreshed from the inert ones
   u64 *keys_out;
   u32 *vals_out;
   u32 *lst_out;
@@ -324,15 +354,12 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_gather(const GatherArgs
       const bool lv = (w[k] & RANK_DEAD) == 0u;
       bool so = lv;
       if (lv && a.filter && is_huge_label(w[k])) {
-        // rho* of (group, round): the first member to ask decides
-        u64 *cell = a.rho + (w[k] / HUGE_M);
-        u64 e = ld_volatile_u64(cell);
-        if ((u32)(e >> 32) != a.round) {
-          const u64 want = ((u64)a.round << 32) | r2[k];
-          const u64 old = atomicCAS(reinterpret_cast<unsigned long long *>(cell), (unsigned long long)e, (unsigned long long)want);
-          e = (old == e) ? want : old;
+        const u64 e = __ldg(a.rho + (w[k] / HUGE_M));
+        if ((u32)(e >> 32) == a.round && (u32)e == r2[k]) {
+          so = false;  // inert: shares the group's dominant key
+          // a few of them per round volunteer as next round's representative
+          if (k == 0 && chunk == blockIdx.x) a.rep[w[k] / HUGE_M] = sfx[k];
         }
-        so = (u32)e != r2[k];
       }
       const u64 kx = so ? (((u64)w[k] << a.lab_bits) | r2[k]) : 0ull;
       const u32 ml = __ballot_sync(0xffffffffu, lv), ms = __ballot_sync(0xffffffffu, so);
@@ -651,6 +678,7 @@ struct RebuildArgs {
   u64 *G;              // [n + 2] slot range of every live group, indexed by its label
   u32 *hlist;          // labels of the huge groups created in this round are appended here
   u32 *hcount;
+  u32 *rep;            // [n / HUGE_M + 2] their first member becomes the representative
   ulonglong2 *status;  // [tiles] x = flag(2) | head+1 ; y = flag(2) | survivors(31) | groups(31)
   u32 *survivors;      // [1] k_tail_summary: number of elements that stay live after this round
   u32 *tile_tail;      // [tiles] k_tail_summary: first tail slot inside the tile (or NO_TAIL)
@@ -933,7 +961,10 @@ __global__ void __launch_bounds__(THREADS, 2) k_rebuild(const RebuildArgs a) {
         if (!keep) a.rank[sx[j + 1]] = lab;
         if ((f >> j) & 1u) {  // group head: publish the group's slot range
           a.G[lab] = (u64)(s1 - 1u) | ((u64)(e1 - 1u) << 32);
-          if (!keep && is_huge_label(lab)) a.hlist[atomicAdd(a.hcount, 1u)] = lab;
+          if (!keep && is_huge_label(lab)) {
+            a.hlist[atomicAdd(a.hcount, 1u)] = lab;
+            a.rep[lab / HUGE_M] = sx[j + 1];
+          }
         }
         if (MODE == RB_SPARSE) a.SA[px[j]] = (i32)sx[j + 1];
         ++c;
@@ -973,7 +1004,7 @@ struct Layout {
   u64 *packed; u64 packed_words;
   u64 *keys[2]; u32 *vals[2]; u32 *slots; u32 *lst[2]; u32 *rank;
   u64 *G;                      // [n + 2] slot range of every live group, indexed by label
-  u64 *state, *rho;            // [n / HUGE_M + 2] per huge label
+  u64 *state, *rho; u32 *rep;  // [n / HUGE_M + 2] per huge label
   u32 *hlist[2]; u32 hcap;     // labels of the huge groups
   u32 *hcount;                 // [2]
   u32 *gupd; u32 *gupd_count;  // end-of-inert-block updates of one round
@@ -1003,6 +1034,7 @@ Layout make_layout(char *base, u32 n) {
   y.G = c.take<u64>(N + 2);
   y.state = c.take<u64>(N / HUGE_M + 2);
   y.rho = c.take<u64>(N / HUGE_M + 2);
+  y.rep = c.take<u32>(N / HUGE_M + 2);
   y.hcap = (u32)(2 * (N / HUGE_T) + 4096);
   y.hlist[0] = c.take<u32>(y.hcap); y.hlist[1] = c.take<u32>(y.hcap);
   y.hcount = c.take<u32>(64);
@@ -1244,6 +1276,7 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
   GSA_TRY(cudaMemsetAsync(y.state, 0, ((size_t)n / HUGE_M + 2) * sizeof(u64), st));
   GSA_TRY(cudaMemsetAsync(y.rho, 0, ((size_t)n / HUGE_M + 2) * sizeof(u64), st));
   GSA_TRY(cudaMemsetAsync(y.hcount, 0, 2 * sizeof(u32), st));
+  GSA_TRY(cudaMemsetAsync(y.rep, 0xff, ((size_t)n / HUGE_M + 2) * sizeof(u32), st));
   // tail summaries + survivor count, then the rebuild proper.  *survivors_out is known before the
   // rebuild is launched, which lets the last round skip its rank writes.
   auto launch_rebuild = [&](bool round0, u32 L, int kv, bool may_finish, u32 *survivors_out) -> int {
@@ -1257,7 +1290,7 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
     r.short_from = round0 ? (n - ns) : 0xffffffffu;
     r.lab_bits = lab_bits;
     r.rank = y.rank; r.SA = d_SA;
-    r.G = y.G; r.hlist = y.hlist[hcur]; r.hcount = y.hcount + hcur;
+    r.G = y.G; r.hlist = y.hlist[hcur]; r.hcount = y.hcount + hcur; r.rep = y.rep;
     r.status = y.rb_status;
     r.survivors = y.survivors;
     r.tile_tail = y.tile_tail; r.next_tail = y.next_tail;
@@ -1325,19 +1358,24 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
     if (hc > y.hcap / 2) { set_error("huge-group list overflow", __FILE__, __LINE__); return GSA_ECUDA; }
     GSA_TRY(cudaMemsetAsync(y.hcount + (hcur ^ 1), 0, sizeof(u32), st));
     if (hc) {
-      k_huge_prepare<<<(u32)div_up(hc, 256), 256, 0, st>>>(y.hlist[hcur], hc, y.G, y.state, round, y.hlist[hcur ^ 1], y.hcount + (hcur ^ 1));
+      k_huge_prepare<<<(u32)div_up(hc, 256), 256, 0, st>>>(y.hlist[hcur], hc, y.G, y.state, y.rep, round, y.hlist[hcur ^ 1], y.hcount + (hcur ^ 1));
       KLAUNCH_CHECK();
       if (stats) stats->kernel_launches++;
     }
     hcur ^= 1;  // the rebuild of this round appends the huge groups it creates to the new list
     const bool filter = filter_allowed && !sparse && hc > 0;
+    if (filter) {
+      k_huge_rho<<<(u32)div_up(hc, 256), 256, 0, st>>>(y.hlist[hcur], y.hcount + hcur, y.rank, y.state, y.rep, y.rho, round, h, n);
+      KLAUNCH_CHECK();
+      if (stats) stats->kernel_launches++;
+    }
     GSA_TRY(cudaMemsetAsync(y.ghist, 0, MAX_PASSES * RADIX * sizeof(u32), st));
     GSA_TRY(cudaMemsetAsync(y.live_counter, 0, 2 * sizeof(u32), st));
     GatherArgs g;
     g.lst_in = ident ? nullptr : y.lst[lcur];
     g.Lin = Lcand; g.rank = y.rank; g.SA = d_SA; g.n = n; g.h = h; g.lab_bits = lab_bits;
     g.npass = sparse ? 0 : npass;  // sparse: keys are completed by k_lazy_fill, histogram afterwards
-    g.round = round; g.filter = filter ? 1 : 0; g.state = y.state; g.rho = y.rho;
+    g.round = round; g.filter = filter ? 1 : 0; g.state = y.state; g.rho = y.rho; g.rep = y.rep;
     g.keys_out = y.keys[0]; g.vals_out = y.vals[0]; g.lst_out = y.lst[lcur ^ 1];
     g.counter = y.live_counter; g.ghist = y.ghist;
     g.sa0 = sparse ? d_SA : nullptr;
