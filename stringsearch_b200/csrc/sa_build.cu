@@ -110,6 +110,58 @@ __global__ void __launch_bounds__(THREADS) k_hist0(const KeyGen g, int npass, u3
     if (shist[i]) atomicAdd(&ghist[i], shist[i]);
 }
 
+// When a radix digit covers whole symbols (8 % b == 0, key_bits % 8 == 0) every digit of every
+// round-0 key is one of the n 8-bit windows W[j] = stream bits [j*b, j*b + 8): digit p of
+// suffix i is W[i + s_p] with s_p = (key_bits - 8(p+1)) / b.  So one 256-bin histogram of the
+// windows replaces the npass histograms (one shared-memory atomic per suffix instead of
+// npass), up to the few windows at the two ends that k_hist0_finish corrects.
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) k_hist0_windows(const u64 *__restrict__ packed, u32 n, u32 b, u32 *__restrict__ hfull) {
+  __shared__ u32 shist[RADIX];
+  for (int i = threadIdx.x; i < RADIX; i += THREADS) shist[i] = 0;
+  __syncthreads();
+  const u32 stride = gridDim.x * THREADS;
+  const u32 iters = (n + stride - 1) / stride;
+  u32 j = blockIdx.x * THREADS + threadIdx.x;
+  for (u32 it = 0; it < iters; ++it, j += stride) {
+    const bool valid = j < n;
+    u64 win = 0;
+    if (valid) {
+      const u64 bit = (u64)j * b;
+      const u64 w = bit >> 6;
+      const u32 sh = (u32)bit & 63u;
+      const u64 w0 = __ldg(packed + w), w1 = __ldg(packed + w + 1);
+      win = (sh ? ((w0 << sh) | (w1 >> (64u - sh))) : w0) >> 56;
+    }
+    hist_add(shist, win, valid, 1);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < RADIX; i += THREADS)
+    if (shist[i]) atomicAdd(&hfull[i], shist[i]);
+}
+
+__global__ void __launch_bounds__(RADIX) k_hist0_finish(const u64 *__restrict__ packed, u32 n, u32 b, u32 key_bits, int npass,
+                                                        const u32 *__restrict__ hfull, u32 *__restrict__ ghist) {
+  const u32 v = threadIdx.x;
+  const u32 full = hfull[v];
+  for (int p = 0; p < npass; ++p) ghist[p * RADIX + v] = full;
+  __syncthreads();
+  if (v == 0) {
+    for (int p = 0; p < npass; ++p) {
+      const u32 sp = (key_bits - 8u * (u32)(p + 1)) / b;  // suffix i reads window i + sp
+      // windows 0 .. sp-1 belong to no suffix; windows n .. n+sp-1 (all zero) do
+      for (u32 j = 0; j < sp && j < n; ++j) {
+        const u64 bit = (u64)j * b;
+        const u32 sh = (u32)bit & 63u;
+        const u64 w0 = packed[bit >> 6], w1 = packed[(bit >> 6) + 1];
+        const u32 win = (u32)((sh ? ((w0 << sh) | (w1 >> (64u - sh))) : w0) >> 56);
+        ghist[p * RADIX + win] -= 1u;
+      }
+      ghist[p * RADIX + 0] += min(sp, n);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------
 // Repetitiveness probe: how many of `m` pseudo-random suffixes share their first
 // key_bits / b symbols with another sampled suffix?  (Open-addressing insert into a small
@@ -197,6 +249,37 @@ __device__ __forceinline__ u32 resolve_label(u32 w, const u64 *__restrict__ stat
   const u32 code = (u32)st;
   if (code & STATE_FINAL) { *fin = true; return code & RANK_MASK; }
   return code;  // moved to a new label
+}
+
+// Round 0 creates the huge groups of a repetitive text: scattering a label to each of their
+// members would be n random 4-byte writes.  Instead the group head registers
+// (round-0 key -> label) in a small hash table and k_rank_huge0 walks the text once, in order:
+// a suffix whose key is in the table gets its label by a streaming write.
+struct HugeKeyTable {
+  u64 *keys;    // [cap]
+  u32 *labels;  // [cap] 0 = empty
+  u32 mask;     // cap - 1
+};
+__device__ __forceinline__ u32 hkt_hash(u64 key, u32 mask) { return (u32)((key * 0x9E3779B97F4A7C15ull) >> 40) & mask; }
+__device__ __forceinline__ void hkt_insert(const HugeKeyTable &t, u64 key, u32 label) {
+  u32 sl = hkt_hash(key, t.mask);
+  for (;;) {
+    if (atomicCAS(t.labels + sl, 0u, label) == 0u) { t.keys[sl] = key; return; }
+    sl = (sl + 1u) & t.mask;
+  }
+}
+__global__ void __launch_bounds__(256) k_rank_huge0(const KeyGen g, const HugeKeyTable t, u32 first_short, u32 *__restrict__ rank) {
+  const u32 stride = gridDim.x * blockDim.x;
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < first_short; i += stride) {
+    const u64 key = key_of_suffix(g, i);
+    u32 sl = hkt_hash(key, t.mask);
+    for (;;) {
+      const u32 lab = __ldg(t.labels + sl);
+      if (lab == 0u) break;
+      if (__ldg(t.keys + sl) == key) { rank[i] = lab; break; }
+      sl = (sl + 1u) & t.mask;
+    }
+  }
 }
 
 // Once per round, one thread per huge group: classify it, publish the verdict in STATE for the
@@ -679,6 +762,7 @@ struct RebuildArgs {
   u32 *hlist;          // labels of the huge groups created in this round are appended here
   u32 *hcount;
   u32 *rep;            // [n / HUGE_M + 2] their first member becomes the representative
+  HugeKeyTable hkt;    // round 0: huge groups register their key here (k_rank_huge0 labels the members)
   ulonglong2 *status;  // [tiles] x = flag(2) | head+1 ; y = flag(2) | survivors(31) | groups(31)
   u32 *survivors;      // [1] k_tail_summary: number of elements that stay live after this round
   u32 *tile_tail;      // [tiles] k_tail_summary: first tail slot inside the tile (or NO_TAIL)
@@ -958,12 +1042,14 @@ __global__ void __launch_bounds__(THREADS, 2) k_rebuild(const RebuildArgs a) {
         const bool inert_owner = (hr >> j) & 1u;  // the old label stays with the run's inert block
         const bool keep = !ROUND0 && !inert_owner && old >= s1 && old <= e1;
         const u32 lab = keep ? old : pick_label(s1 - 1u, e1 - 1u, inert_owner ? old : 0u);
-        if (!keep) a.rank[sx[j + 1]] = lab;
+        const bool by_table = ROUND0 && is_huge_label(lab);  // members are labelled by k_rank_huge0
+        if (!keep && !by_table) a.rank[sx[j + 1]] = lab;
         if ((f >> j) & 1u) {  // group head: publish the group's slot range
           a.G[lab] = (u64)(s1 - 1u) | ((u64)(e1 - 1u) << 32);
           if (!keep && is_huge_label(lab)) {
             a.hlist[atomicAdd(a.hcount, 1u)] = lab;
             a.rep[lab / HUGE_M] = sx[j + 1];
+            if (ROUND0) hkt_insert(a.hkt, kx[j + 1], lab);
           }
         }
         if (MODE == RB_SPARSE) a.SA[px[j]] = (i32)sx[j + 1];
@@ -1005,6 +1091,8 @@ struct Layout {
   u64 *keys[2]; u32 *vals[2]; u32 *slots; u32 *lst[2]; u32 *rank;
   u64 *G;                      // [n + 2] slot range of every live group, indexed by label
   u64 *state, *rho; u32 *rep;  // [n / HUGE_M + 2] per huge label
+  u64 *hkt_keys; u32 *hkt_labels; u32 hkt_cap;  // round-0 key -> label of the huge groups
+  u32 *hfull;                  // [256] window histogram of round 0
   u32 *hlist[2]; u32 hcap;     // labels of the huge groups
   u32 *hcount;                 // [2]
   u32 *gupd; u32 *gupd_count;  // end-of-inert-block updates of one round
@@ -1035,6 +1123,11 @@ Layout make_layout(char *base, u32 n) {
   y.state = c.take<u64>(N / HUGE_M + 2);
   y.rho = c.take<u64>(N / HUGE_M + 2);
   y.rep = c.take<u32>(N / HUGE_M + 2);
+  y.hkt_cap = 1024;
+  while (y.hkt_cap < 4 * (N / HUGE_T + 1)) y.hkt_cap <<= 1;
+  y.hkt_keys = c.take<u64>(y.hkt_cap);
+  y.hkt_labels = c.take<u32>(y.hkt_cap);
+  y.hfull = c.take<u32>(RADIX);
   y.hcap = (u32)(2 * (N / HUGE_T) + 4096);
   y.hlist[0] = c.take<u32>(y.hcap); y.hlist[1] = c.take<u32>(y.hcap);
   y.hcount = c.take<u32>(64);
@@ -1248,6 +1341,7 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
   }
   if (k < 1) k = 1;
   if (k > k_max) k = k_max;
+  if (8 % b == 0 && !getenv("GSA_KEY_SYMBOLS")) k = std::min<u32>(k_max, (k + 8 / b - 1) / (8 / b) * (8 / b));  // whole digits
   const u32 key_bits = k * b;
   const u32 ns = (k - 1 < n) ? (k - 1) : n;           // short suffixes
   if (stats) {
@@ -1260,9 +1354,18 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
   const int npass0 = (int)div_up(key_bits, 8);
   const u32 hist_blocks = (u32)std::min<u64>((u64)sms * 4, std::max<u64>(1, div_up(n, HIST_THREADS)));
   GSA_TRY(cudaMemsetAsync(y.ghist, 0, MAX_PASSES * RADIX * sizeof(u32), st));
-  k_hist0<HIST_THREADS><<<hist_blocks, HIST_THREADS, 0, st>>>(gen, npass0, y.ghist);
-  KLAUNCH_CHECK();
-  if (stats) stats->kernel_launches++;
+  if (8 % b == 0 && key_bits % 8 == 0 && n > 64) {
+    GSA_TRY(cudaMemsetAsync(y.hfull, 0, RADIX * sizeof(u32), st));
+    k_hist0_windows<HIST_THREADS><<<hist_blocks, HIST_THREADS, 0, st>>>(y.packed, n, b, y.hfull);
+    KLAUNCH_CHECK();
+    k_hist0_finish<<<1, RADIX, 0, st>>>(y.packed, n, b, key_bits, npass0, y.hfull, y.ghist);
+    KLAUNCH_CHECK();
+    if (stats) stats->kernel_launches += 2;
+  } else {
+    k_hist0<HIST_THREADS><<<hist_blocks, HIST_THREADS, 0, st>>>(gen, npass0, y.ghist);
+    KLAUNCH_CHECK();
+    if (stats) stats->kernel_launches++;
+  }
   int cur = 0;
   u32 passes = 0;
   PassTimer timer;
@@ -1291,6 +1394,7 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
     r.lab_bits = lab_bits;
     r.rank = y.rank; r.SA = d_SA;
     r.G = y.G; r.hlist = y.hlist[hcur]; r.hcount = y.hcount + hcur; r.rep = y.rep;
+    r.hkt = HugeKeyTable{y.hkt_keys, y.hkt_labels, y.hkt_cap - 1};
     r.status = y.rb_status;
     r.survivors = y.survivors;
     r.tile_tail = y.tile_tail; r.next_tail = y.next_tail;
@@ -1322,7 +1426,14 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
   };
 
   u32 survivors = 0;
+  GSA_TRY(cudaMemsetAsync(y.hkt_labels, 0, (size_t)y.hkt_cap * sizeof(u32), st));
   GSA_TRY_RC(launch_rebuild(true, n, cur, true, &survivors));
+  if (survivors >= HUGE_T) {  // there may be huge groups: label their members in text order
+    const u32 blocks = (u32)std::min<u64>((u64)sms * 8, std::max<u64>(1, div_up(n, 256)));
+    k_rank_huge0<<<blocks, 256, 0, st>>>(gen, HugeKeyTable{y.hkt_keys, y.hkt_labels, y.hkt_cap - 1}, n - ns, y.rank);
+    KLAUNCH_CHECK();
+    if (stats) stats->kernel_launches++;
+  }
   GSA_TRY(cudaEventRecord(ev[3], st));
   GSA_TRY(cudaStreamSynchronize(st));
   u32 round = 0;
