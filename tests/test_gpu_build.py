@@ -57,6 +57,12 @@ def test_every_length_up_to_80(port):
     ("two_symbols_nul_1M", lambda s: (s.random_bytes(1 << 20, 9) & 1).astype(np.uint8)),
     ("five_symbols_1M", lambda s: (s.random_bytes(1 << 20, 10) % 5).astype(np.uint8)),
     ("text_like_2M", lambda s: (s.random_bytes(2 << 20, 11) % 27 + 97).astype(np.uint8)),
+    # huge groups (>= 65536 suffixes sharing a prefix): the inert-majority path of the doubling rounds
+    ("rep7_4M", lambda s: s.repetitive(4 << 20, 5, period=7, mutation_rate=1e-4)),
+    ("rep40_6M_rare", lambda s: s.repetitive(6 << 20, 6, period=40, mutation_rate=3e-6)),
+    ("run_in_random_4M", lambda s: np.concatenate([s.random_bytes(1 << 20, 12), np.full(2 << 20, 65, np.uint8), s.random_bytes(1 << 20, 13)])),
+    ("two_runs_3M", lambda s: np.concatenate([np.full(1 << 20, 66, np.uint8), s.random_bytes(1 << 20, 14), np.full(1 << 20, 66, np.uint8)])),
+    ("square_4M", lambda s: np.tile(s.random_bytes(1 << 20, 15), 4)),
 ])
 def test_structured_inputs_match_reference(ref, name, maker):
     from stringsearch_b200 import synth
@@ -107,6 +113,24 @@ def test_sparse_mode_on_and_off(port, monkeypatch):
             _assert_same(_sort(t), exp, f"sparse off, key_symbols={ks}")
     monkeypatch.delenv("GSA_NO_SPARSE", raising=False)
     monkeypatch.delenv("GSA_KEY_SYMBOLS", raising=False)
+
+
+def test_inert_filter_on_and_off(ref, monkeypatch):
+    """GSA_NO_INERT=1 sorts every live suffix in every round (no huge-group filter): same SA."""
+    from stringsearch_b200 import synth
+    from stringsearch_b200 import _native as N
+
+    t = synth.repetitive(3 << 20, 21, period=11, mutation_rate=2e-5)
+    exp = ref.sa_build(t)
+    st_on, st_off = N.BuildStats(), N.BuildStats()
+    monkeypatch.delenv("GSA_NO_INERT", raising=False)
+    _assert_same(_sort(t, st_on), exp, "filter on")
+    monkeypatch.setenv("GSA_NO_INERT", "1")
+    _assert_same(_sort(t, st_off), exp, "filter off")
+    monkeypatch.delenv("GSA_NO_INERT", raising=False)
+    on = sum(r["sorted"] for r in st_on.rounds_list()[1:])
+    off = sum(r["sorted"] for r in st_off.rounds_list()[1:])
+    assert on < off // 2, (on, off)  # the filter really skipped most of the sorting work
 
 
 def test_tile_boundaries(port):
