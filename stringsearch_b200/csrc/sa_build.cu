@@ -239,16 +239,22 @@ __device__ __forceinline__ u32 pick_label(u32 s, u32 e, u32 avoid) {
   return mid;
 }
 
-// rank word -> current label; *fin = the suffix is (or has just become) unique.
-__device__ __forceinline__ u32 resolve_label(u32 w, const u64 *__restrict__ state, u32 round, bool *fin) {
+// rank word -> current label; *fin = the suffix is (or has just become) unique.  `st` is the
+// STATE entry of the word's label (only looked at for live huge labels), so that callers can
+// issue the table loads of many words before resolving any of them.
+__device__ __forceinline__ bool needs_state(u32 w) { return !(w & RANK_DEAD) && w != 0u && is_huge_label(w); }
+__device__ __forceinline__ u32 resolve_with(u32 w, u64 st, u32 round, bool *fin) {
   *fin = false;
   if (w & RANK_DEAD) { *fin = true; return w & RANK_MASK; }
   if (!is_huge_label(w)) return w;
-  const u64 st = __ldg(state + (w / HUGE_M));
   if ((u32)(st >> 32) != round) return w;  // nothing happened to this group
   const u32 code = (u32)st;
   if (code & STATE_FINAL) { *fin = true; return code & RANK_MASK; }
   return code;  // moved to a new label
+}
+__device__ __forceinline__ u32 resolve_label(u32 w, const u64 *__restrict__ state, u32 round, bool *fin) {
+  const u64 st = needs_state(w) ? __ldg(state + (w / HUGE_M)) : 0ull;
+  return resolve_with(w, st, round, fin);
 }
 
 // Round 0 creates the huge groups of a repetitive text: scattering a label to each of their
@@ -412,12 +418,17 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_gather(const GatherArgs
       const u64 t = (u64)sfx[k] + a.h;
       r2[k] = (!(w[k] & RANK_DEAD) && t < a.n) ? __ldcg(a.rank + t) : 0u;
     }
-    // resolve huge labels through this round's verdicts; members fix their own entry
+    // resolve huge labels through this round's verdicts; members fix their own entry.  The table
+    // loads of all IPT rows are issued together, three times: STATE of the suffix, STATE of
+    // suffix + h, rho* of the (resolved) group.
+    u64 tb[IPT];
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) tb[k] = needs_state(w[k]) ? __ldg(a.state + (w[k] / HUGE_M)) : 0ull;
 #pragma unroll
     for (int k = 0; k < IPT; ++k) {
       if (!(w[k] & RANK_DEAD)) {
         bool fin;
-        const u32 lab = resolve_label(w[k], a.state, a.round, &fin);
+        const u32 lab = resolve_with(w[k], tb[k], a.round, &fin);
         if (fin) {  // its huge group has shrunk to this one suffix
           a.SA[lab - 1u] = (i32)sfx[k];
           a.rank[sfx[k]] = RANK_DEAD | lab;
@@ -425,10 +436,19 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_gather(const GatherArgs
         } else {
           if (lab != w[k]) a.rank[sfx[k]] = lab;
           w[k] = lab;
-          if (r2[k] != 0u) r2[k] = resolve_label(r2[k], a.state, a.round, &fin);
         }
       }
     }
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) tb[k] = (!(w[k] & RANK_DEAD) && needs_state(r2[k])) ? __ldg(a.state + (r2[k] / HUGE_M)) : 0ull;
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) {
+      bool fin;
+      if (!(w[k] & RANK_DEAD) && r2[k] != 0u) r2[k] = resolve_with(r2[k], tb[k], a.round, &fin);
+    }
+#pragma unroll
+    for (int k = 0; k < IPT; ++k)
+      tb[k] = (a.filter && !(w[k] & RANK_DEAD) && is_huge_label(w[k])) ? __ldg(a.rho + (w[k] / HUGE_M)) : 0ull;
     u32 offl[IPT], offs[IPT];  // slot offsets inside the warp's output runs (live list, sort input)
     u32 srt = 0;               // bit k: element k goes to the sort
     u32 wl = 0, ws = 0;
@@ -437,7 +457,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_gather(const GatherArgs
       const bool lv = (w[k] & RANK_DEAD) == 0u;
       bool so = lv;
       if (lv && a.filter && is_huge_label(w[k])) {
-        const u64 e = __ldg(a.rho + (w[k] / HUGE_M));
+        const u64 e = tb[k];
         if ((u32)(e >> 32) == a.round && (u32)e == r2[k]) {
           so = false;  // inert: shares the group's dominant key
           // a few of them per round volunteer as next round's representative
