@@ -220,6 +220,7 @@ constexpr u32 HUGE_M = 256;
 constexpr u32 HUGE_T = 1u << 16;
 static_assert(HUGE_T >= 2 * HUGE_M, "a huge range must hold two candidate labels");
 constexpr u32 STATE_FINAL = 0x80000000u;
+constexpr u32 HUGE_REPS = 8;  // representatives per huge group: rho* is the plurality of their second key halves
 
 __device__ __forceinline__ bool is_huge_label(u32 lab) { return (lab & (HUGE_M - 1u)) == 0u; }
 
@@ -307,7 +308,7 @@ __global__ void __launch_bounds__(256) k_huge_prepare(const u32 *__restrict__ hi
     G[nl] = g;
     state[lab / HUGE_M] = tag | nl;
     if (is_huge_label(nl)) {
-      rep[nl / HUGE_M] = rep[lab / HUGE_M];
+      for (u32 x = 0; x < HUGE_REPS; ++x) rep[(nl / HUGE_M) * HUGE_REPS + x] = rep[(lab / HUGE_M) * HUGE_REPS + x];
       hout[atomicAdd(hout_count, 1u)] = nl;
     }
     return;
@@ -315,8 +316,11 @@ __global__ void __launch_bounds__(256) k_huge_prepare(const u32 *__restrict__ hi
   hout[atomicAdd(hout_count, 1u)] = lab;
 }
 
-// After the verdicts: rho* of every huge group for this round = label(rep + h), provided the
-// representative still belongs to the group (otherwise the group goes unfiltered this round).
+// After the verdicts: rho* of every huge group for this round = the most frequent label(rep + h)
+// among its representatives that still belong to the group (none left: the group goes
+// unfiltered this round).  One representative would do for correctness, but its key half is the
+// dominant one only with the probability that a member is inert, and a miss costs a full sort
+// of the group.
 __global__ void __launch_bounds__(256) k_huge_rho(const u32 *__restrict__ hl, const u32 *__restrict__ hl_count,
                                                   const u32 *__restrict__ rank, const u64 *__restrict__ state,
                                                   const u32 *__restrict__ rep, u64 *__restrict__ rho, u32 round, u64 h,
@@ -324,19 +328,31 @@ __global__ void __launch_bounds__(256) k_huge_rho(const u32 *__restrict__ hl, co
   const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= *hl_count) return;
   const u32 lab = hl[j];
-  const u32 r = rep[lab / HUGE_M];
-  if (r >= n) return;
-  bool fin;
-  const u32 w = rank[r];
-  if (w == 0u || resolve_label(w, state, round, &fin) != lab || fin) return;
-  const u64 t = (u64)r + h;
-  u32 r2 = 0;
-  if (t < n) {
-    const u32 w2 = rank[t];
-    if (w2 == 0u) return;  // sparse mode keeps no label for it
-    r2 = resolve_label(w2, state, round, &fin);
+  u32 val[HUGE_REPS];
+  u32 nv = 0;
+  for (u32 x = 0; x < HUGE_REPS; ++x) {
+    const u32 r = rep[(lab / HUGE_M) * HUGE_REPS + x];
+    if (r >= n) continue;
+    bool fin;
+    const u32 w = rank[r];
+    if (w == 0u || resolve_label(w, state, round, &fin) != lab || fin) continue;
+    const u64 t = (u64)r + h;
+    u32 r2 = 0;
+    if (t < n) {
+      const u32 w2 = rank[t];
+      if (w2 == 0u) continue;  // sparse mode keeps no label for it
+      r2 = resolve_label(w2, state, round, &fin);
+    }
+    val[nv++] = r2;
   }
-  rho[lab / HUGE_M] = ((u64)round << 32) | r2;
+  if (nv == 0) return;
+  u32 best = val[0], bestc = 0;
+  for (u32 x = 0; x < nv; ++x) {
+    u32 c = 0;
+    for (u32 y = 0; y < nv; ++y) c += (val[y] == val[x]) ? 1u : 0u;
+    if (c > bestc) { bestc = c; best = val[x]; }
+  }
+  rho[lab / HUGE_M] = ((u64)round << 32) | best;
 }
 
 struct GatherArgs {
@@ -352,7 +368,7 @@ struct GatherArgs {
   int filter;         // elect rho* and leave inert members out of the sort
   const u64 *state;   // [n / HUGE_M + 2] verdicts of k_huge_prepare, tagged with the round
   const u64 *rho;     // [n / HUGE_M + 2] round << 32 | rho*  (k_huge_rho)
-  u32 *rep;           // [n / HUGE_M + 2] a member of every huge group, refreshed from the inert ones
+  u32 *rep;           // [n / HUGE_M + 2][HUGE_REPS] members of every huge group, refreshed from the inert ones
   u64 *keys_out;
   u32 *vals_out;
   u32 *lst_out;
@@ -461,7 +477,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_gather(const GatherArgs
         if ((u32)(e >> 32) == a.round && (u32)e == r2[k]) {
           so = false;  // inert: shares the group's dominant key
           // a few of them per round volunteer as next round's representative
-          if (k == 0 && chunk == blockIdx.x) a.rep[w[k] / HUGE_M] = sfx[k];
+          if (k == 0 && chunk == blockIdx.x) a.rep[(w[k] / HUGE_M) * HUGE_REPS + ((blockIdx.x + warp) % HUGE_REPS)] = sfx[k];
         }
       }
       const u64 kx = so ? (((u64)w[k] << a.lab_bits) | r2[k]) : 0ull;
@@ -1068,7 +1084,7 @@ __global__ void __launch_bounds__(THREADS, 2) k_rebuild(const RebuildArgs a) {
           a.G[lab] = (u64)(s1 - 1u) | ((u64)(e1 - 1u) << 32);
           if (!keep && is_huge_label(lab)) {
             a.hlist[atomicAdd(a.hcount, 1u)] = lab;
-            a.rep[lab / HUGE_M] = sx[j + 1];
+            a.rep[(lab / HUGE_M) * HUGE_REPS] = sx[j + 1];  // the other slots are filled by inert volunteers
             if (ROUND0) hkt_insert(a.hkt, kx[j + 1], lab);
           }
         }
@@ -1142,7 +1158,7 @@ Layout make_layout(char *base, u32 n) {
   y.G = c.take<u64>(N + 2);
   y.state = c.take<u64>(N / HUGE_M + 2);
   y.rho = c.take<u64>(N / HUGE_M + 2);
-  y.rep = c.take<u32>(N / HUGE_M + 2);
+  y.rep = c.take<u32>((N / HUGE_M + 2) * HUGE_REPS);
   y.hkt_cap = 1024;
   while (y.hkt_cap < 4 * (N / HUGE_T + 1)) y.hkt_cap <<= 1;
   y.hkt_keys = c.take<u64>(y.hkt_cap);
@@ -1399,7 +1415,7 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
   GSA_TRY(cudaMemsetAsync(y.state, 0, ((size_t)n / HUGE_M + 2) * sizeof(u64), st));
   GSA_TRY(cudaMemsetAsync(y.rho, 0, ((size_t)n / HUGE_M + 2) * sizeof(u64), st));
   GSA_TRY(cudaMemsetAsync(y.hcount, 0, 2 * sizeof(u32), st));
-  GSA_TRY(cudaMemsetAsync(y.rep, 0xff, ((size_t)n / HUGE_M + 2) * sizeof(u32), st));
+  GSA_TRY(cudaMemsetAsync(y.rep, 0xff, ((size_t)n / HUGE_M + 2) * HUGE_REPS * sizeof(u32), st));
   // tail summaries + survivor count, then the rebuild proper.  *survivors_out is known before the
   // rebuild is launched, which lets the last round skip its rank writes.
   auto launch_rebuild = [&](bool round0, u32 L, int kv, bool may_finish, u32 *survivors_out) -> int {
