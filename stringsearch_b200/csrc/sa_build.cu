@@ -1107,9 +1107,9 @@ constexpr int RB_THREADS = 512;
 constexpr int RB_IPT = 8;
 constexpr int RB_TILE = RB_THREADS * RB_IPT;
 constexpr int HIST_THREADS = 512;
-constexpr int GA_THREADS = 256;
+constexpr int GA_THREADS = 512;
 constexpr int GA_IPT = 8;
-constexpr int GA_BLOCKS_PER_SM = 4;
+constexpr int GA_BLOCKS_PER_SM = 2;
 
 struct Carve {
   char *p;
