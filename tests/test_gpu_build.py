@@ -115,6 +115,51 @@ def test_sparse_mode_on_and_off(port, monkeypatch):
     monkeypatch.delenv("GSA_KEY_SYMBOLS", raising=False)
 
 
+def test_fuzz_repetitive_structures(ref):
+    """Randomised periodic / run-heavy / copy-heavy texts around the huge-group threshold (65 536
+    suffixes per group): every combination of verdicts (label moved, group became small, unique,
+    vanished), several huge groups interacting, NUL-heavy alphabets."""
+    from stringsearch_b200 import _native as N
+
+    rng = np.random.default_rng(20261017)
+    for case in range(36):
+        n = int(rng.integers(150_000, 1_500_000))
+        kind = case % 6
+        if kind == 0:      # short period, sparse mutations
+            per = int(rng.integers(1, 40))
+            x = np.tile(rng.integers(0, 256, per, dtype=np.uint8), n // per + 1)[:n].copy()
+            m = int(rng.integers(0, 60))
+            x[rng.integers(0, n, m)] = rng.integers(0, 256, m, dtype=np.uint8)
+        elif kind == 1:    # a few long runs of the same byte inside random text
+            x = rng.integers(0, 4, n, dtype=np.uint8)
+            for _ in range(int(rng.integers(1, 4))):
+                a = int(rng.integers(0, n - 100_000))
+                x[a:a + int(rng.integers(70_000, 400_000))] = int(rng.integers(0, 2))
+        elif kind == 2:    # the same block copied many times, with a few edits per copy
+            blk = rng.integers(0, 256, int(rng.integers(1_000, 20_000)), dtype=np.uint8)
+            x = np.tile(blk, n // blk.size + 1)[:n].copy()
+            m = int(rng.integers(0, 200))
+            x[rng.integers(0, n, m)] = rng.integers(0, 256, m, dtype=np.uint8)
+        elif kind == 3:    # two interleaved periodic texts over {0, 1} (NUL is a symbol)
+            p1, p2 = int(rng.integers(2, 9)), int(rng.integers(2, 9))
+            a = np.tile(rng.integers(0, 2, p1, dtype=np.uint8), n // p1 + 1)[:n]
+            b = np.tile(rng.integers(0, 2, p2, dtype=np.uint8), n // p2 + 1)[:n]
+            cut = int(rng.integers(n // 4, 3 * n // 4))
+            x = np.concatenate([a[:cut], b[cut:]])
+        elif kind == 4:    # all one byte, except a handful of positions
+            x = np.full(n, int(rng.integers(0, 256)), np.uint8)
+            m = int(rng.integers(0, 6))
+            x[rng.integers(0, n, m)] = rng.integers(0, 256, m, dtype=np.uint8)
+        else:              # Fibonacci-like word (many nested repeats)
+            a, b = b"a", b"ab"
+            while len(b) < n:
+                a, b = b, b + a
+            x = np.frombuffer(b[:n], dtype=np.uint8).copy()
+        st = N.BuildStats()
+        got = _sort(x, st)
+        _assert_same(got, ref.sa_build(x), f"fuzz case {case} kind {kind} n={n}")
+
+
 def test_inert_filter_on_and_off(ref, monkeypatch):
     """GSA_NO_INERT=1 sorts every live suffix in every round (no huge-group filter): same SA."""
     from stringsearch_b200 import synth
