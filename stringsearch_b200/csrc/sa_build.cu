@@ -487,7 +487,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_gather(const GatherArgs
       wl += (u32)__popc(ml);
       ws += (u32)__popc(ms);
       srt |= (so ? 1u : 0u) << k;
-      hist_add(shist, kx, so, a.npass);
+      if (ms) hist_add(shist, kx, so, a.npass);  // warp-uniform: rows of inert members skip it
     }
     if (lane == 0) { s_wl[warp] = wl; s_ws[warp] = ws; }
     __syncthreads();
@@ -1373,6 +1373,10 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
     GSA_TRY(cudaMemcpyAsync(&dups, y.survivors, sizeof(u32), cudaMemcpyDeviceToHost, st));
     GSA_TRY(cudaStreamSynchronize(st));
     if (dups > M / 8) k = k_max;
+    // ... and if the sampled suffixes fall into very few classes the text consists of a few huge
+    // groups: those are cheap to refine (their inert majority is not sorted), so a 32-bit start
+    // saves half of the round-0 passes for the price of one cheap extra round.
+    if (M - dups < M / 16 && !getenv("GSA_NO_INERT")) k = std::max<u32>(1, std::min<u32>(k_max, 32 / b));
     if (stats) stats->kernel_launches++;
   }
   if (k < 1) k = 1;
