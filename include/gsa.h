@@ -94,6 +94,18 @@ size_t gsa_build_workspace_bytes(int32_t n);
 int32_t gsa_build_device(const uint8_t *d_T, int32_t *d_SA, int32_t n, void *workspace, size_t workspace_bytes,
                          void *stream, gsa_build_stats *stats);
 
+/* Burrows-Wheeler transform.
+ * gsa_divbwt replaces divbwt(T, U, A, n) (c-sources/divsufsort.c:372-405, divsufsort.h): same
+ * signature, output convention and return value (the primary index; -1 bad arguments, -2 out
+ * of memory; n <= 1 -> n).  `A` is scratch in the reference and is ignored (may be NULL).  HOST
+ * pointers.  gsa_bwt_device is the device-pointer form of bw_transform (utils.c:52-110) for a
+ * suffix array that is already resident: U[0] = T[n-1], then T[SA[i]-1] for SA[i] != 0 in SA
+ * order; *primary_index = slot of suffix 0, plus one.
+ * (inverse_bw_transform is a sequential LF-mapping walk and is not part of the GPU path.) */
+int32_t gsa_divbwt(const uint8_t *T, uint8_t *U, int32_t *A, int32_t n);
+int32_t gsa_bwt_device(const uint8_t *d_T, const int32_t *d_SA, int32_t n, uint8_t *d_U, int32_t *primary_index,
+                       void *stream);
+
 /* O(n) validity check of a suffix array on the GPU (device pointers).
  * Replaces sacabase::verify (crates/sacabase/src/lib.rs:127-149) / sufcheck
  * (c-sources/utils.c:160-241) at sizes where the O(n * LCP) pairwise check is

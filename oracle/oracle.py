@@ -215,6 +215,16 @@ class _Ref:
         L.sufcheck.restype = C.c_int32
         L.sa_search.argtypes = [_u8p, C.c_int32, _u8p, C.c_int32, _i32p, C.c_int32, _i32p]
         L.sa_search.restype = C.c_int32
+        L.divbwt.argtypes = [_u8p, _u8p, _i32p, C.c_int32]
+        L.divbwt.restype = C.c_int32
+
+    def divbwt(self, text):
+        """reference divbwt -> (U, primary index)"""
+        t = _as_u8(text)
+        u = np.empty(t.size, dtype=np.uint8)
+        tp = _ptr(t, _u8p) if t.size else _ptr(np.zeros(1, np.uint8), _u8p)
+        up = _ptr(u, _u8p) if u.size else _ptr(np.zeros(1, np.uint8), _u8p)
+        return u, self.lib.divbwt(tp, up, None, t.size)
 
     def divsufsort_raw(self, tptr, saptr, n) -> int:
         return self.lib.divsufsort(tptr, saptr, n)

@@ -92,6 +92,8 @@ def _load() -> C.CDLL:
         "gsa_divsufsort_ex": ([vp, vp, C.c_int32, C.c_int32, C.POINTER(BuildStats)], C.c_int32),
         "gsa_build_workspace_bytes": ([C.c_int32], C.c_size_t),
         "gsa_build_device": ([vp, vp, C.c_int32, vp, C.c_size_t, vp, C.POINTER(BuildStats)], C.c_int32),
+        "gsa_divbwt": ([vp, vp, vp, C.c_int32], C.c_int32),
+        "gsa_bwt_device": ([vp, vp, C.c_int32, vp, i32p, vp], C.c_int32),
         "gsa_sufcheck_device": ([vp, vp, C.c_int32, vp, i64p], C.c_int32),
         "gsa_sufcheck": ([vp, vp, C.c_int32, C.c_int32, i64p], C.c_int32),
         "gsa_index_create": ([vp, C.c_int64, C.c_int32, C.POINTER(vp), C.POINTER(BuildStats)], C.c_int32),

@@ -246,6 +246,40 @@ int32_t gsa_divsufsort(const uint8_t *T, int32_t *SA, int32_t n) {
   return gsa_divsufsort_ex(T, SA, n, current_device(), nullptr);
 }
 
+// divbwt(T, U, A, n) (c-sources/divsufsort.c:372-405): `A` is only scratch in the reference and is
+// ignored here (the SA is built in device memory).  Host pointers.
+int32_t gsa_divbwt(const uint8_t *T, uint8_t *U, int32_t *A, int32_t n) {
+  (void)A;
+  if (T == nullptr || U == nullptr || n < 0) return GSA_EINVAL;
+  if (n <= 1) { if (n == 1) U[0] = T[0]; return n; }
+  const int device = current_device();
+  DeviceGuard dg(device);
+  if (!dg.ok) return GSA_ECUDA;
+  Stream st;
+  GSA_TRY_RC(st.create());
+  const size_t text_bytes = align_up((size_t)n + 64, 256), sa_bytes = align_up((size_t)n * sizeof(i32), 256);
+  const size_t ws_bytes = std::max(build_workspace_bytes((u32)n), text_bytes);
+  Scratch sc;
+  GSA_TRY_RC(sc.acquire(device, text_bytes + sa_bytes + ws_bytes));
+  u8 *d_T = reinterpret_cast<u8 *>(sc.p);
+  i32 *d_SA = reinterpret_cast<i32 *>(sc.p + text_bytes);
+  char *d_ws = sc.p + text_bytes + sa_bytes;
+  GSA_TRY(cudaMemcpyAsync(d_T, T, (size_t)n, cudaMemcpyHostToDevice, st.s));
+  GSA_TRY_RC(build_sa_device(d_T, d_SA, (u32)n, d_ws, ws_bytes, st.s, nullptr));
+  u8 *d_U = reinterpret_cast<u8 *>(d_ws);  // the sort workspace is free again
+  i32 pidx = 0;
+  GSA_TRY_RC(bwt_device(d_T, d_SA, (u32)n, d_U, &pidx, st.s));
+  GSA_TRY(cudaMemcpyAsync(U, d_U, (size_t)n, cudaMemcpyDeviceToHost, st.s));
+  GSA_TRY(cudaStreamSynchronize(st.s));
+  return pidx;
+}
+
+int32_t gsa_bwt_device(const uint8_t *d_T, const int32_t *d_SA, int32_t n, uint8_t *d_U, int32_t *primary_index,
+                       void *stream) {
+  if (n < 0 || (n > 0 && (!d_T || !d_SA || !d_U))) return GSA_EINVAL;
+  return bwt_device(d_T, d_SA, (u32)n, d_U, primary_index, static_cast<cudaStream_t>(stream));
+}
+
 int32_t gsa_sufcheck_device(const uint8_t *d_T, const int32_t *d_SA, int32_t n, void *stream, int64_t *bad_index) {
   if (n < 0 || (n > 0 && (d_T == nullptr || d_SA == nullptr))) return GSA_EINVAL;
   return sufcheck_device(d_T, d_SA, (u32)n, static_cast<cudaStream_t>(stream), bad_index);

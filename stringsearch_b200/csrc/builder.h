@@ -2,6 +2,8 @@
 #pragma once
 #include <string.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace gsa {
@@ -19,6 +21,9 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
 // verify.cu
 size_t sufcheck_workspace_bytes(u32 n);
 int sufcheck_device(const u8 *d_T, const i32 *d_SA, u32 n, cudaStream_t st, i64 *bad_index);
+
+// bwt.cu
+int bwt_device(const u8 *d_T, const i32 *d_SA, u32 n, u8 *d_U, i32 *primary_index, cudaStream_t st);
 
 // search.cu
 // Text view of an index: the suffix array covers text[0, n); text_avail >= n bytes are

@@ -140,8 +140,8 @@ __device__ __forceinline__ u32 peers_by_ballot(u32 d) {
   return m;
 }
 
-template <int THREADS, int IPT, bool GEN>
-__global__ void __launch_bounds__(THREADS, 3) k_radix_pass(const PassArgs a) {
+template <int THREADS, int IPT, bool GEN, int MIN_BLOCKS = 3>
+__global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_radix_pass(const PassArgs a) {
   static_assert(THREADS >= RADIX && THREADS % 32 == 0, "one thread per bin is assumed");
   static_assert(IPT % 2 == 0 && 32 * IPT <= 65535, "warp-local ranks are packed as u16 pairs");
   constexpr int WARPS = THREADS / 32;

@@ -1178,7 +1178,7 @@ Layout make_layout(char *base, u32 n) {
   y.live_counter = c.take<u32>(64);
   y.survivors = c.take<u32>(64);
   y.result = c.take<RoundResult>(16);
-  const size_t ptiles = div_up(N, PASS_TILE);
+  const size_t ptiles = div_up(N, 3072);  // smallest tile of the pass configurations
   y.pass_status_words = 256 + ptiles * RADIX;
   y.pass_status = c.take<u32>(y.pass_status_words);
   const size_t rtiles = div_up(N, RB_TILE);
@@ -1239,11 +1239,14 @@ static int run_passes(const Layout &y, u32 L, int npass, int cur, const KeyGen *
   GSA_TRY(cudaStreamSynchronize(st));
   const u32 tiles = (u32)div_up(L, PASS_TILE);
   const size_t smem = PassCfg<PASS_THREADS, PASS_IPT>::SMEM;
+  const char *cfg_env = getenv("GSA_PASS_CFG");  // experiments: alternative tile shapes of the pass kernel
+  const int pass_cfg = cfg_env ? atoi(cfg_env) : 0;
+  const u32 tiles_max = (u32)div_up(L, 3072);
   bool need_gen = gen != nullptr;
   u32 done = 0;
   for (int p = 0; p < npass; ++p) {
     if (((skip >> p) & 1u) && !(need_gen && p == npass - 1)) continue;  // constant digit: identity pass
-    GSA_TRY(cudaMemsetAsync(y.pass_status, 0, (256 + (size_t)tiles * RADIX) * sizeof(u32), st));
+    GSA_TRY(cudaMemsetAsync(y.pass_status, 0, (256 + (size_t)(pass_cfg ? tiles_max : tiles) * RADIX) * sizeof(u32), st));
     PassArgs a;
     a.n = L;
     a.shift = 8u * (u32)p;
@@ -1265,7 +1268,15 @@ static int run_passes(const Layout &y, u32 L, int npass, int cur, const KeyGen *
       a.keys_in = y.keys[cur]; a.vals_in = y.vals[cur];
       a.keys_out = y.keys[cur ^ 1]; a.vals_out = y.vals[cur ^ 1];
       a.gen = KeyGen{};
-      k_radix_pass<PASS_THREADS, PASS_IPT, false><<<tiles, PASS_THREADS, smem, st>>>(a);
+      if (pass_cfg == 1) {
+        k_radix_pass<256, 12, false, 4><<<(u32)div_up(L, 256 * 12), 256, PassCfg<256, 12>::SMEM, st>>>(a);
+      } else if (pass_cfg == 2) {
+        k_radix_pass<384, 16, false, 2><<<(u32)div_up(L, 384 * 16), 384, PassCfg<384, 16>::SMEM, st>>>(a);
+      } else if (pass_cfg == 3) {
+        k_radix_pass<512, 12, false, 2><<<(u32)div_up(L, 512 * 12), 512, PassCfg<512, 12>::SMEM, st>>>(a);
+      } else {
+        k_radix_pass<PASS_THREADS, PASS_IPT, false><<<tiles, PASS_THREADS, smem, st>>>(a);
+      }
       cur ^= 1;
     }
     KLAUNCH_CHECK();
@@ -1293,6 +1304,9 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
     const int smem = (int)PassCfg<PASS_THREADS, PASS_IPT>::SMEM;
     GSA_TRY(cudaFuncSetAttribute(k_radix_pass<PASS_THREADS, PASS_IPT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     GSA_TRY(cudaFuncSetAttribute(k_radix_pass<PASS_THREADS, PASS_IPT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    GSA_TRY(cudaFuncSetAttribute(k_radix_pass<256, 12, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PassCfg<256, 12>::SMEM));
+    GSA_TRY(cudaFuncSetAttribute(k_radix_pass<384, 16, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PassCfg<384, 16>::SMEM));
+    GSA_TRY(cudaFuncSetAttribute(k_radix_pass<512, 12, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PassCfg<512, 12>::SMEM));
   }
   char *owned = nullptr;
   const size_t need = build_workspace_bytes(n);

@@ -43,3 +43,14 @@ def sort(text, device: int | None = None, stats: N.BuildStats | None = None) -> 
     sa = np.zeros(t.size, dtype=np.int32)
     sort_in_place(t, sa, device=device, stats=stats)
     return SuffixArray(t, sa)
+
+
+def bwt(text):
+    """divbwt (crates/cdivsufsort/c-sources/divsufsort.c:372-405): -> (U, primary_index)."""
+    t = N.as_u8(text)
+    assert t.size < I32_MAX, f"text too large, should not exceed {I32_MAX - 1} bytes"
+    u = np.empty(t.size, dtype=np.uint8)
+    rc = N.lib.gsa_divbwt(N.ptr(t) if t.size else N.ptr(np.zeros(1, np.uint8)),
+                          N.ptr(u) if u.size else N.ptr(np.zeros(1, np.uint8)), None, t.size)
+    assert rc >= 0, f"divbwt returned {rc}: {N.last_error()}"
+    return u, rc

@@ -178,6 +178,18 @@ def test_inert_filter_on_and_off(ref, monkeypatch):
     assert on < off // 2, (on, off)  # the filter really skipped most of the sorting work
 
 
+def test_bwt_matches_reference(ref, sa_golden):
+    """gsa_divbwt vs the reference's divbwt (divsufsort.c:372-405): same string, same primary index."""
+    from stringsearch_b200 import divsufsort, synth
+
+    texts = [t for _, t, _ in sa_golden] + [synth.acgt(300_000, 2), synth.repetitive(500_000, 3, period=60),
+                                            synth.random_bytes(100_001, 4), np.zeros(70_000, np.uint8)]
+    for t in texts:
+        u, pidx = divsufsort.bwt(t)
+        eu, epidx = ref.divbwt(t)
+        assert pidx == epidx and (u == eu).all(), (len(t), pidx, epidx)
+
+
 def test_tile_boundaries(port):
     """Sizes straddling the radix tile (4096), rebuild tile (2048) and vector widths."""
     rng = np.random.default_rng(7)
