@@ -300,3 +300,31 @@ def test_full_size_rep_1G_properties():
     assert N.lib.gsa_sufcheck_device(d_t.data_ptr(), d_sa.data_ptr(), t.size, stream, C.byref(bad)) == 0, bad.value
     assert stats.rounds >= 10
     print("rep_1G", stats.ms_total, "ms", [(r["depth"], r["live"], r["passes"]) for r in stats.rounds_list()])
+
+
+@pytest.mark.timeout(1800)
+def test_largest_supported_text_properties():
+    """n = 2^31 - 2, the largest text the reference accepts (crates/divsufsort/src/divsufsort.rs:9-13:
+    `text.len() < i32::MAX`): 32-bit index arithmetic at the limit.  Random bytes generated on the
+    device; checked with the O(n) GPU sufcheck.  Needs ~130 GB of HBM (skipped if not free)."""
+    import torch
+    from stringsearch_b200 import _native as N
+
+    n = 2**31 - 2
+    free, _ = torch.cuda.mem_get_info()
+    need = N.lib.gsa_build_workspace_bytes(n) + 10 * n + (4 << 30)
+    if free < need:
+        pytest.skip(f"needs {need >> 30} GiB of free device memory, have {free >> 30}")
+    g = torch.Generator(device="cuda")
+    g.manual_seed(7)
+    d_t = torch.randint(0, 256, (n,), dtype=torch.uint8, device="cuda", generator=g)
+    d_t[1_000_000:1_200_000] = 7          # a run: a huge group next to the unique suffixes
+    d_t[-5:] = 0                          # NULs at the very end: short-suffix ordering
+    d_sa = torch.empty(n, dtype=torch.int32, device="cuda")
+    stats = N.BuildStats()
+    stream = torch.cuda.current_stream().cuda_stream
+    rc = N.lib.gsa_build_device(d_t.data_ptr(), d_sa.data_ptr(), n, None, 0, stream, C.byref(stats))
+    assert rc == 0, N.last_error()
+    bad = C.c_int64(-1)
+    assert N.lib.gsa_sufcheck_device(d_t.data_ptr(), d_sa.data_ptr(), n, stream, C.byref(bad)) == 0, bad.value
+    print("n=2^31-2:", stats.ms_total, "ms", [(r["depth"], r["live"], r["sorted"], r["passes"]) for r in stats.rounds_list()])
