@@ -43,7 +43,8 @@ extern "C" {
 
 /* Per-round log of one SA construction (one entry per prefix-doubling round).
  * The harness uses it to recompute the roofline:
- * algorithmic bytes of round k = live * 52 + sorted * 24 * passes (round 0: n * (41 + 24 * passes)). */
+ * algorithmic bytes of round k = live * 52 + sorted * 24 * passes + bag * 32
+ * (round 0: n * (41 + 24 * passes)). */
 typedef struct gsa_round_stat {
   uint64_t depth;      /* symbols of every suffix known to be sorted AFTER this round */
   uint64_t live;       /* live (not yet unique) suffixes walked in this round */
@@ -53,6 +54,8 @@ typedef struct gsa_round_stat {
   uint32_t sorted;     /* suffixes actually sorted (live minus the inert members of huge groups) */
   float ms_total;      /* device time of the whole round */
   float ms_sort;       /* ... of which radix passes */
+  uint32_t bag;        /* suffixes of tiny groups refined outside the sort (the bag) in this round */
+  uint32_t reserved_;
 } gsa_round_stat;
 
 typedef struct gsa_build_stats {

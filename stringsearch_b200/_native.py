@@ -33,6 +33,8 @@ class RoundStat(C.Structure):
         ("sorted", C.c_uint32),
         ("ms_total", C.c_float),
         ("ms_sort", C.c_float),
+        ("bag", C.c_uint32),
+        ("reserved_", C.c_uint32),
     ]
 
 
@@ -55,19 +57,21 @@ class BuildStats(C.Structure):
     def rounds_list(self):
         return [
             dict(depth=int(r.depth), live=int(r.live), sorted=int(r.sorted), groups=int(r.groups), key_bits=int(r.key_bits),
-                 passes=int(r.passes), ms_total=float(r.ms_total), ms_sort=float(r.ms_sort))
+                 passes=int(r.passes), ms_total=float(r.ms_total), ms_sort=float(r.ms_sort), bag=int(r.bag))
             for r in list(self.round)[: min(self.rounds, GSA_MAX_ROUNDS)]
         ]
 
     def algorithmic_bytes(self) -> int:
-        """round 0 n*(41+24p); round k>=1 L*52 + S*24p, where S <= L is the
-        number of suffixes actually sorted (inert members of huge groups are walked, not sorted)."""
+        """round 0 n*(41+24p); round k>=1 L*52 + S*24p + B*32, where S <= L is the
+        number of suffixes actually sorted (inert members of huge groups are walked, not sorted) and
+        B the suffixes of tiny groups refined in the bag (suffix, slot, label gather, key half out and
+        in, suffix + slot out, SA: 8 words of 4 bytes)."""
         total = 0
         for i, r in enumerate(self.rounds_list()):
             if i == 0:
                 total += r["live"] * (41 + 24 * r["passes"])
             else:
-                total += r["live"] * 52 + r["sorted"] * 24 * r["passes"]
+                total += r["live"] * 52 + r["sorted"] * 24 * r["passes"] + r["bag"] * 32
         return total
 
 

@@ -10,7 +10,7 @@ namespace gsa {
 
 struct RoundResult {
   u32 live_out;    // suffixes still in non-singleton groups after the round
-  u32 groups_out;  // number of such groups
+  u32 bag_out;     // of which moved to the bag by this rebuild
 };
 
 // sa_build.cu

@@ -224,20 +224,42 @@ constexpr u32 HUGE_REPS = 8;  // representatives per huge group: rho* is the plu
 
 __device__ __forceinline__ bool is_huge_label(u32 lab) { return (lab & (HUGE_M - 1u)) == 0u; }
 
-// Label (1-based slot) for the group occupying slots [s, e], e > s: the middle of the range,
-// moved to a multiple of HUGE_M for huge groups and off such a multiple for small ones.
+// The BAG.  A suffix whose group has at most TINY_MAX members leaves the text-order walk and
+// the radix sort for good: such groups are kept, group by group, as (suffix, slot) entries in
+// a list and refined in place every round -- gather label(i + h), sort inside the group
+// (k_bag_refine, one thread per entry), split, finalise.  For these suffixes a round costs one
+// random 4-byte gather instead of 8 radix passes over 12 bytes.
+// The class of a group is readable from its label alone:
+//   multiple of HUGE_M : huge   (>= HUGE_T slots), state in the group tables
+//   other even label   : medium, sorted through the text-order path every round
+//   odd label          : tiny, lives in the bag; always the canonical label of its slot range
+// (tiny_max == 0 switches the tiny class off: sparse mode, which keeps no label for most suffixes.)
+constexpr u32 TINY_MAX = 64;
+constexpr u32 BAG_HEAD = 0x80000000u;  // bag entry: first member of its group
+
+__device__ __forceinline__ u32 tiny_label(u32 s) { return (s & 1u) ? s + 2u : s + 1u; }  // first odd label in [s+1, ..]
+
+// Label (1-based slot) for the group occupying slots [s, e], e > s.
 // `avoid`: a label that must not be chosen (the label of the huge group this one is split
 // from: its table entry still belongs to the inert block); 0 = none.
-__device__ __forceinline__ u32 pick_label(u32 s, u32 e, u32 avoid) {
+__device__ __forceinline__ u32 pick_label(u32 s, u32 e, u32 avoid, u32 tiny_max) {
+  const u32 size = e - s + 1u;
   const u32 mid = s + ((e - s) >> 1) + 1u;
-  if (e - s + 1u >= HUGE_T) {
+  if (size >= HUGE_T) {
     u32 lab = mid & ~(HUGE_M - 1u);
     if (lab < s + 1u) lab += HUGE_M;
     if (lab == avoid) lab = (lab + HUGE_M <= e + 1u) ? lab + HUGE_M : lab - HUGE_M;
     return lab;
   }
-  if (is_huge_label(mid)) return (mid + 1u <= e + 1u) ? mid + 1u : mid - 1u;
-  return mid;
+  if (size <= tiny_max) return tiny_label(s);
+  u32 lab = mid;
+  if (tiny_max == 0u) {  // any label that is no multiple of HUGE_M
+    if (is_huge_label(lab)) lab = (lab + 1u <= e + 1u) ? lab + 1u : lab - 1u;
+    return lab;
+  }
+  if (lab & 1u) lab = (lab + 1u <= e + 1u) ? lab + 1u : lab - 1u;      // size > TINY_MAX: room on both sides
+  if (is_huge_label(lab)) lab = (lab + 2u <= e + 1u) ? lab + 2u : lab - 2u;
+  return lab;
 }
 
 // rank word -> current label; *fin = the suffix is (or has just become) unique.  `st` is the
@@ -293,7 +315,7 @@ __global__ void __launch_bounds__(256) k_rank_huge0(const KeyGen g, const HugeKe
 // readers of this round, and rebuild the list of huge groups.
 __global__ void __launch_bounds__(256) k_huge_prepare(const u32 *__restrict__ hin, u32 cnt, u64 *__restrict__ G,
                                                       u64 *__restrict__ state, u32 *__restrict__ rep, u32 round,
-                                                      u32 *__restrict__ hout, u32 *__restrict__ hout_count) {
+                                                      u32 tiny_max, u32 *__restrict__ hout, u32 *__restrict__ hout_count) {
   const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= cnt) return;
   const u32 lab = hin[j];
@@ -304,7 +326,10 @@ __global__ void __launch_bounds__(256) k_huge_prepare(const u32 *__restrict__ hi
   if (size <= 0) return;  // every member left the inert block
   if (size == 1) { state[lab / HUGE_M] = tag | STATE_FINAL | (u32)(gs + 1); return; }
   if (size < (i64)HUGE_T || !((i64)lab >= gs + 1 && (i64)lab <= ge + 1)) {
-    const u32 nl = pick_label((u32)gs, (u32)ge, 0u);  // small label, or a new huge one inside the range
+    // new huge label inside the range, or the label of the class the group has shrunk to (if tiny,
+    // its members -- still in the text-order list -- are all sorted this round and the rebuild
+    // moves them to the bag)
+    const u32 nl = pick_label((u32)gs, (u32)ge, 0u, tiny_max);
     G[nl] = g;
     state[lab / HUGE_M] = tag | nl;
     if (is_huge_label(nl)) {
@@ -365,7 +390,8 @@ struct GatherArgs {
   u32 lab_bits;
   int npass;
   u32 round;
-  int filter;         // elect rho* and leave inert members out of the sort
+  int filter;         // leave inert members of huge groups out of the sort
+  u32 tiny_max;       // > 0: suffixes with an odd label live in the bag and are dropped from the list
   const u64 *state;   // [n / HUGE_M + 2] verdicts of k_huge_prepare, tagged with the round
   const u64 *rho;     // [n / HUGE_M + 2] round << 32 | rho*  (k_huge_rho)
   u32 *rep;           // [n / HUGE_M + 2][HUGE_REPS] members of every huge group, refreshed from the inert ones
@@ -428,6 +454,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_gather(const GatherArgs
     for (int k = 0; k < IPT; ++k) {
       w[k] = (sfx[k] != 0xffffffffu) ? __ldcg(a.rank + sfx[k]) : RANK_DEAD;
       if (w[k] == 0u) w[k] = RANK_DEAD;  // sparse mode: unique since round 0
+      if (a.tiny_max && (w[k] & 1u)) w[k] = RANK_DEAD;  // tiny group: handled in the bag from now on
     }
 #pragma unroll
     for (int k = 0; k < IPT; ++k) {
@@ -799,7 +826,10 @@ struct RebuildArgs {
   u32 *hcount;
   u32 *rep;            // [n / HUGE_M + 2] their first member becomes the representative
   HugeKeyTable hkt;    // round 0: huge groups register their key here (k_rank_huge0 labels the members)
-  ulonglong2 *status;  // [tiles] x = flag(2) | head+1 ; y = flag(2) | survivors(31) | groups(31)
+  u32 tiny_max;        // groups of at most this many suffixes move to the bag (0: no bag)
+  u64 *bag_desc;       // (first slot | size << 32) of every tiny group formed by this rebuild
+  u32 *bag_desc_count;
+  ulonglong2 *status;  // [tiles] x = flag(2) | head+1 ; y = flag(2) | survivors(31) | moved to the bag(31)
   u32 *survivors;      // [1] k_tail_summary: number of elements that stay live after this round
   u32 *tile_tail;      // [tiles] k_tail_summary: first tail slot inside the tile (or NO_TAIL)
   const u32 *next_tail;  // [tiles] k_tail_scan: first tail slot in any later tile
@@ -1047,7 +1077,6 @@ __global__ void __launch_bounds__(THREADS, 2) k_rebuild(const RebuildArgs a) {
       s_pre[0] = xh; s_pre[1] = xc; s_pre[2] = xg;
       if ((u64)(tile + 1) * TILE >= L) {  // last tile: totals of the round
         a.result->live_out = xc + bc;
-        a.result->groups_out = xg + bg;
       }
     }
   }
@@ -1076,16 +1105,26 @@ __global__ void __launch_bounds__(THREADS, 2) k_rebuild(const RebuildArgs a) {
       } else {
         const u32 old = ROUND0 ? 0u : (u32)(kx[j + 1] >> a.lab_bits);
         const bool inert_owner = (hr >> j) & 1u;  // the old label stays with the run's inert block
-        const bool keep = !ROUND0 && !inert_owner && old >= s1 && old <= e1;
-        const u32 lab = keep ? old : pick_label(s1 - 1u, e1 - 1u, inert_owner ? old : 0u);
+        const u32 size = e1 - s1 + 1u;
+        const bool tiny = size <= a.tiny_max;
+        // a medium group keeps its label while the label stays inside its range; huge labels are owned
+        // by inert blocks, tiny groups always carry the canonical label of their range
+        const bool keep = !ROUND0 && !inert_owner && !tiny && size < HUGE_T && old >= s1 && old <= e1 &&
+                          !is_huge_label(old) && (a.tiny_max == 0u || !(old & 1u));
+        const u32 lab = keep ? old : pick_label(s1 - 1u, e1 - 1u, inert_owner ? old : 0u, a.tiny_max);
         const bool by_table = ROUND0 && is_huge_label(lab);  // members are labelled by k_rank_huge0
-        if (!keep && !by_table) a.rank[sx[j + 1]] = lab;
+        if (lab != old && !by_table) a.rank[sx[j + 1]] = lab;
+        if (tiny) a.SA[px[j]] = (i32)sx[j + 1];  // provisional order: the bag is backed by SA
         if ((f >> j) & 1u) {  // group head: publish the group's slot range
-          a.G[lab] = (u64)(s1 - 1u) | ((u64)(e1 - 1u) << 32);
-          if (!keep && is_huge_label(lab)) {
-            a.hlist[atomicAdd(a.hcount, 1u)] = lab;
-            a.rep[(lab / HUGE_M) * HUGE_REPS] = sx[j + 1];  // the other slots are filled by inert volunteers
-            if (ROUND0) hkt_insert(a.hkt, kx[j + 1], lab);
+          if (tiny) {
+            a.bag_desc[atomicAdd(a.bag_desc_count, 1u)] = (u64)(s1 - 1u) | ((u64)size << 32);
+          } else {
+            a.G[lab] = (u64)(s1 - 1u) | ((u64)(e1 - 1u) << 32);
+            if (!keep && is_huge_label(lab)) {
+              a.hlist[atomicAdd(a.hcount, 1u)] = lab;
+              a.rep[(lab / HUGE_M) * HUGE_REPS] = sx[j + 1];  // the other slots are filled by inert volunteers
+              if (ROUND0) hkt_insert(a.hkt, kx[j + 1], lab);
+            }
           }
         }
         if (MODE == RB_SPARSE) a.SA[px[j]] = (i32)sx[j + 1];
@@ -1093,6 +1132,126 @@ __global__ void __launch_bounds__(THREADS, 2) k_rebuild(const RebuildArgs a) {
       }
     }
   }
+}
+
+// ------------------------------------------------------------------------------------
+// The bag (see pick_label): tiny groups, refined without the radix sort.
+//   k_bag_append   descriptors written by a rebuild -> flattened (suffix, slot | HEAD) entries
+//   k_bag_gather   r2 = label(suffix + h) for every entry (the one random read of the round)
+//   k_bag_refine   one thread per entry, one block per 960 entries (+ 64 of overlap, so that a
+//                  group never straddles a block): order the members of each group by r2 (rank
+//                  by counting, groups have <= 64 members), split into runs of equal r2,
+//                  finalise the unique ones, re-label and re-append the others.
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_bag_append(const u64 *__restrict__ desc, const u32 *__restrict__ desc_count,
+                                                    const i32 *__restrict__ SA, u32 *__restrict__ bag_sufx,
+                                                    u32 *__restrict__ bag_pos, u32 *__restrict__ bag_count) {
+  const u32 q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= *desc_count) return;
+  const u64 d = desc[q];
+  const u32 s = (u32)d, size = (u32)(d >> 32);
+  const u32 base = atomicAdd(bag_count, size);
+  for (u32 j = 0; j < size; ++j) {
+    bag_sufx[base + j] = (u32)SA[s + j];
+    bag_pos[base + j] = (s + j) | (j == 0 ? BAG_HEAD : 0u);
+  }
+}
+
+__global__ void __launch_bounds__(256) k_bag_gather(const u32 *__restrict__ bag_sufx, u32 nb, const u32 *__restrict__ rank,
+                                                    const u64 *__restrict__ state, u32 round, u64 h, u32 n,
+                                                    u32 *__restrict__ r2out) {
+  const u32 stride = gridDim.x * blockDim.x;
+  for (u32 l = blockIdx.x * blockDim.x + threadIdx.x; l < nb; l += stride) {
+    const u64 t = (u64)__ldg(bag_sufx + l) + h;
+    u32 r2 = 0;
+    if (t < n) {
+      bool fin;
+      r2 = resolve_label(__ldcg(rank + t), state, round, &fin);
+    }
+    r2out[l] = r2;
+  }
+}
+
+constexpr int BAG_TILE = 960;
+constexpr int BAG_THREADS = BAG_TILE + (int)TINY_MAX;  // 1024
+
+struct BagArgs {
+  const u32 *sufx_in, *pos_in, *r2;
+  u32 nb;
+  u32 *sufx_out, *pos_out, *count_out;
+  u32 *rank;
+  i32 *SA;
+};
+
+__global__ void __launch_bounds__(BAG_THREADS, 1) k_bag_refine(const BagArgs a) {
+  __shared__ u32 s_sfx[BAG_THREADS], s_pos[BAG_THREADS], s_r2[BAG_THREADS];
+  __shared__ u32 s_slot[BAG_THREADS];  // new slot, bit 31 = survives (its run has more than one member)
+  __shared__ u32 s_excl[BAG_THREADS];  // survivors before this entry (block order)
+  __shared__ u32 s_warp[BAG_THREADS / 32];
+  __shared__ u32 s_base;
+  const u32 tid = threadIdx.x;
+  const u32 l = blockIdx.x * (u32)BAG_TILE + tid;
+  const bool have = l < a.nb;
+  s_sfx[tid] = have ? a.sufx_in[l] : 0u;
+  s_pos[tid] = have ? a.pos_in[l] : BAG_HEAD;  // past the end: looks like the start of another group
+  s_r2[tid] = have ? a.r2[l] : 0u;
+  __syncthreads();
+  // my group: [g0, g1) in block coordinates; it belongs to this block iff its head is below BAG_TILE
+  u32 g0 = tid;
+  while (!(s_pos[g0] & BAG_HEAD) && g0 > 0) --g0;
+  const bool head_seen = (s_pos[g0] & BAG_HEAD) != 0u;  // false: the head is in the previous block
+  u32 g1 = tid + 1;
+  while (g1 < (u32)BAG_THREADS && !(s_pos[g1] & BAG_HEAD)) ++g1;
+  const bool mine = have && head_seen && g0 < (u32)BAG_TILE;
+  u32 less = 0, eq = 0, eq_before = 0;
+  const u32 my = s_r2[tid];
+  if (mine) {
+    for (u32 m = g0; m < g1; ++m) {
+      const u32 v = s_r2[m];
+      less += (v < my) ? 1u : 0u;
+      eq += (v == my) ? 1u : 0u;
+      eq_before += (v == my && m < tid) ? 1u : 0u;
+    }
+  }
+  const u32 gs = s_pos[g0] & ~BAG_HEAD;           // first slot of the old group
+  const u32 s1 = gs + less, slot = s1 + eq_before;  // first slot of my run, my own slot
+  const bool surv = mine && eq > 1u;
+  s_slot[tid] = mine ? (slot | (surv ? BAG_HEAD : 0u)) : 0u;
+  // output position: survivors of earlier groups of the block (block order), then the survivors of
+  // my own group in slot order -- the new groups stay contiguous, each headed by its first slot
+  const u32 bal = __ballot_sync(0xffffffffu, surv);
+  if ((tid & 31u) == 0u) s_warp[tid >> 5] = (u32)__popc(bal);
+  __syncthreads();
+  if (tid < 32u) {  // exclusive scan of the 32 warp totals
+    const u32 v = s_warp[tid];
+    u32 inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const u32 t = __shfl_up_sync(0xffffffffu, inc, o);
+      if ((int)tid >= o) inc += t;
+    }
+    s_warp[tid] = inc - v;
+    if (tid == 31u) s_base = inc ? atomicAdd(a.count_out, inc) : 0u;
+  }
+  __syncthreads();
+  s_excl[tid] = s_warp[tid >> 5] + (u32)__popc(bal & ((1u << (tid & 31u)) - 1u));
+  __syncthreads();
+  if (!mine) return;
+  const u32 sufx = s_sfx[tid];
+  if (!surv) {
+    a.SA[slot] = (i32)sufx;
+    a.rank[sufx] = RANK_DEAD | (slot + 1u);
+    return;
+  }
+  u32 in_group_before = 0;
+  for (u32 m = g0; m < g1; ++m) {
+    const u32 sm = s_slot[m];
+    in_group_before += ((sm & BAG_HEAD) && (sm & ~BAG_HEAD) < slot) ? 1u : 0u;
+  }
+  if (tiny_label(s1) != tiny_label(gs)) a.rank[sufx] = tiny_label(s1);
+  const u32 o = s_base + s_excl[g0] + in_group_before;
+  a.sufx_out[o] = sufx;
+  a.pos_out[o] = slot | (slot == s1 ? BAG_HEAD : 0u);
 }
 
 // ------------------------------------------------------------------------------------
@@ -1143,6 +1302,8 @@ struct Layout {
   u32 *pass_status; size_t pass_status_words;  // counter at word 0 (256-word header), then [tiles][256]
   ulonglong2 *rb_status;                       // one 16-byte descriptor per rebuild tile
   u32 *tile_tail, *next_tail;                  // per rebuild tile
+  u32 *bag_sufx[2], *bag_pos[2];               // the bag: (suffix, slot | BAG_HEAD), group after group
+  u32 *bag_count;                              // [0], [1] entries of the two bag buffers, [2] descriptors
   size_t total;
 };
 
@@ -1188,6 +1349,8 @@ Layout make_layout(char *base, u32 n) {
   y.slot_status = c.take<u64>(rtiles + 1);
   y.tile_rtail = c.take<u32>(rtiles + 1);
   y.next_rtail = c.take<u32>(rtiles + 1);
+  for (int i = 0; i < 2; ++i) { y.bag_sufx[i] = c.take<u32>(N); y.bag_pos[i] = c.take<u32>(N); }
+  y.bag_count = c.take<u32>(64);
   y.total = c.used;
   return y;
 }
@@ -1436,6 +1599,10 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
   GSA_TRY(cudaMemsetAsync(y.rep, 0xff, ((size_t)n / HUGE_M + 2) * HUGE_REPS * sizeof(u32), st));
   // tail summaries + survivor count, then the rebuild proper.  *survivors_out is known before the
   // rebuild is launched, which lets the last round skip its rank writes.
+  // The bag is off in sparse mode (most suffixes then carry no label at all).
+  const u32 tiny_conf = getenv("GSA_NO_BAG") ? 0u : TINY_MAX;
+  int bcur = 0;  // bag buffer the rebuild of the current round appends to (= input of the next round)
+  GSA_TRY(cudaMemsetAsync(y.bag_count, 0, 4 * sizeof(u32), st));
   auto launch_rebuild = [&](bool round0, u32 L, int kv, bool may_finish, u32 *survivors_out) -> int {
     const u32 tiles = (u32)div_up(L, RB_TILE);
     GSA_TRY(cudaMemsetAsync(y.rb_status, 0, (size_t)tiles * sizeof(ulonglong2), st));
@@ -1453,20 +1620,26 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
     r.survivors = y.survivors;
     r.tile_tail = y.tile_tail; r.next_tail = y.next_tail;
     r.result = y.result;
+    r.tiny_max = sparse ? 0u : tiny_conf;
+    r.bag_desc = y.keys[kv ^ 1];  // the other half of the sort's double buffer is free until the next walk
+    r.bag_desc_count = y.bag_count + 2;
+    GSA_TRY(cudaMemsetAsync(y.bag_count + 2, 0, sizeof(u32), st));
     if (round0) k_tail_summary<RB_THREADS, RB_IPT, true><<<tiles, RB_THREADS, 0, st>>>(r);
     else k_tail_summary<RB_THREADS, RB_IPT, false><<<tiles, RB_THREADS, 0, st>>>(r);
     KLAUNCH_CHECK();
     k_tail_scan<<<1, 1024, 0, st>>>(y.tile_tail, y.next_tail, tiles);
     KLAUNCH_CHECK();
-    u32 surv = 0;
+    u32 surv = 0, bag_left = 0;
     GSA_TRY(cudaMemcpyAsync(&surv, y.survivors, sizeof(u32), cudaMemcpyDeviceToHost, st));
+    GSA_TRY(cudaMemcpyAsync(&bag_left, y.bag_count + bcur, sizeof(u32), cudaMemcpyDeviceToHost, st));
     GSA_TRY(cudaStreamSynchronize(st));
     *survivors_out = surv;
-    const bool fin = may_finish && surv == 0;  // nothing is live after this round
+    const bool fin = may_finish && surv == 0 && bag_left == 0;  // nothing is live after this round
     if (round0) {
       // few survivors: do not scatter n ranks for the sake of a handful of look-ups
       sparse = surv != 0 && (u64)surv * 64 < n && !getenv("GSA_NO_SPARSE");
       if (sparse) GSA_TRY(cudaMemsetAsync(y.rank, 0, (size_t)n * sizeof(u32), st));
+      r.tiny_max = sparse ? 0u : tiny_conf;
       if (fin) k_rebuild<RB_THREADS, RB_IPT, true, RB_FINAL><<<tiles, RB_THREADS, 0, st>>>(r);
       else if (sparse) k_rebuild<RB_THREADS, RB_IPT, true, RB_SPARSE><<<tiles, RB_THREADS, 0, st>>>(r);
       else k_rebuild<RB_THREADS, RB_IPT, true, RB_NORMAL><<<tiles, RB_THREADS, 0, st>>>(r);
@@ -1476,6 +1649,12 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
     }
     KLAUNCH_CHECK();
     if (stats) stats->kernel_launches += 3;
+    if (r.tiny_max && surv > 1) {  // at most surv / 2 new tiny groups
+      k_bag_append<<<(u32)div_up(surv / 2, 256), 256, 0, st>>>(r.bag_desc, r.bag_desc_count, d_SA, y.bag_sufx[bcur],
+                                                              y.bag_pos[bcur], y.bag_count + bcur);
+      KLAUNCH_CHECK();
+      if (stats) stats->kernel_launches++;
+    }
     return GSA_OK;
   };
 
@@ -1489,20 +1668,22 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
     if (stats) stats->kernel_launches++;
   }
   GSA_TRY(cudaEventRecord(ev[3], st));
+  u32 nbag = 0;  // entries of bag buffer bcur
+  GSA_TRY(cudaMemcpyAsync(&nbag, y.bag_count + bcur, sizeof(u32), cudaMemcpyDeviceToHost, st));
   GSA_TRY(cudaStreamSynchronize(st));
   u32 round = 0;
-  auto log_round = [&](u64 depth, u64 live, u32 sorted, u32 groups, u32 kb, u32 np) {
+  auto log_round = [&](u64 depth, u64 live, u32 sorted, u32 groups, u32 kb, u32 np, u32 bag) {
     const float pass_ms = timer.drain();
     if (!stats) return;
     stats->ms_radix_passes += pass_ms;
     if (round >= GSA_MAX_ROUNDS) return;
     gsa_round_stat &s = stats->round[round];
-    s.depth = depth; s.live = live; s.sorted = sorted; s.groups = groups; s.key_bits = kb; s.passes = np;
+    s.depth = depth; s.live = live; s.sorted = sorted; s.groups = groups; s.key_bits = kb; s.passes = np; s.bag = bag;
     cudaEventElapsedTime(&s.ms_total, ev[0], ev[3]);
     cudaEventElapsedTime(&s.ms_sort, ev[1], ev[2]);
     stats->rounds = round + 1;
   };
-  log_round(k, n, n, 0, key_bits, passes);
+  log_round(k, n, n, 0, key_bits, passes, 0);
 
   // ---- doubling rounds ------------------------------------------------------------------------
   int lcur = 0;        // lst buffer holding the candidates (text order); round 1 uses 0..n-1
@@ -1513,7 +1694,8 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
   const u32 kb = 2 * lab_bits;
   const int npass = (int)div_up(kb, 8);
   const bool filter_allowed = !getenv("GSA_NO_INERT");
-  while (live > 0) {
+  const u32 tiny_max = sparse ? 0u : tiny_conf;
+  while (live > 0 || nbag > 0) {
     ++round;
     GSA_TRY(cudaEventRecord(ev[0], st));
     // huge groups: verdicts for this round, and the list for the next one
@@ -1523,7 +1705,7 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
     if (hc > y.hcap / 2) { set_error("huge-group list overflow", __FILE__, __LINE__); return GSA_ECUDA; }
     GSA_TRY(cudaMemsetAsync(y.hcount + (hcur ^ 1), 0, sizeof(u32), st));
     if (hc) {
-      k_huge_prepare<<<(u32)div_up(hc, 256), 256, 0, st>>>(y.hlist[hcur], hc, y.G, y.state, y.rep, round, y.hlist[hcur ^ 1], y.hcount + (hcur ^ 1));
+      k_huge_prepare<<<(u32)div_up(hc, 256), 256, 0, st>>>(y.hlist[hcur], hc, y.G, y.state, y.rep, round, tiny_max, y.hlist[hcur ^ 1], y.hcount + (hcur ^ 1));
       KLAUNCH_CHECK();
       if (stats) stats->kernel_launches++;
     }
@@ -1540,6 +1722,7 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
     g.lst_in = ident ? nullptr : y.lst[lcur];
     g.Lin = Lcand; g.rank = y.rank; g.SA = d_SA; g.n = n; g.h = h; g.lab_bits = lab_bits;
     g.npass = sparse ? 0 : npass;  // sparse: keys are completed by k_lazy_fill, histogram afterwards
+    g.tiny_max = tiny_max;
     g.round = round; g.filter = filter ? 1 : 0; g.state = y.state; g.rho = y.rho; g.rep = y.rep;
     g.keys_out = y.keys[0]; g.vals_out = y.vals[0]; g.lst_out = y.lst[lcur ^ 1];
     g.counter = y.live_counter; g.ghist = y.ghist;
@@ -1552,6 +1735,23 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
     k_gather<GA_THREADS, GA_IPT, GA_BLOCKS_PER_SM><<<gblocks, GA_THREADS, 0, st>>>(g);
     KLAUNCH_CHECK();
     if (stats) stats->kernel_launches++;
+    // the bag: refine the tiny groups.  Every label read of the round (k_gather, k_bag_gather) precedes
+    // every label write (k_bag_refine, k_rebuild), so all readers see the labels left by the last round.
+    const int bin = bcur;
+    bcur ^= 1;
+    GSA_TRY(cudaMemsetAsync(y.bag_count + bcur, 0, sizeof(u32), st));
+    if (nbag) {
+      const u32 bb = (u32)std::min<u64>((u64)sms * 8, div_up(nbag, 256));
+      k_bag_gather<<<bb, 256, 0, st>>>(y.bag_sufx[bin], nbag, y.rank, y.state, round, h, n, y.slots);
+      KLAUNCH_CHECK();
+      BagArgs ba;
+      ba.sufx_in = y.bag_sufx[bin]; ba.pos_in = y.bag_pos[bin]; ba.r2 = y.slots; ba.nb = nbag;
+      ba.sufx_out = y.bag_sufx[bcur]; ba.pos_out = y.bag_pos[bcur]; ba.count_out = y.bag_count + bcur;
+      ba.rank = y.rank; ba.SA = d_SA;
+      k_bag_refine<<<(u32)div_up(nbag, BAG_TILE), BAG_THREADS, 0, st>>>(ba);
+      KLAUNCH_CHECK();
+      if (stats) stats->kernel_launches += 2;
+    }
     u32 cnt[2] = {0, 0};  // live suffixes found, of which to sort
     GSA_TRY(cudaMemcpyAsync(cnt, y.live_counter, sizeof(cnt), cudaMemcpyDeviceToHost, st));
     GSA_TRY(cudaStreamSynchronize(st));
@@ -1595,10 +1795,13 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
       GSA_TRY_RC(launch_rebuild(false, S, cur, Llive == S, &survivors));
     }
     GSA_TRY(cudaEventRecord(ev[3], st));
+    u32 nbag_next = 0;
+    GSA_TRY(cudaMemcpyAsync(&nbag_next, y.bag_count + bcur, sizeof(u32), cudaMemcpyDeviceToHost, st));
     GSA_TRY(cudaStreamSynchronize(st));
     h *= 2;
-    log_round(h, Llive, S, hc, kb, passes);
-    live = (Llive - S) + survivors;  // inert members + non-unique sorted ones
+    log_round(h, Llive, S, hc, kb, passes, nbag);
+    live = (Llive - S) + survivors;  // inert members + non-unique sorted ones (some of them now in the bag)
+    nbag = nbag_next;
     lcur ^= 1;
     Lcand = Llive;
     ident = false;

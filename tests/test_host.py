@@ -126,6 +126,32 @@ def test_v4_model_matches_oracle(port, sa_golden):
         assert any(inert > 0 for (_, _, _, inert) in st)  # the filter really was exercised
 
 
+def test_v5_model_matches_oracle(port, sa_golden):
+    """tests/model_v5.py: v4 + the bag (tiny groups refined outside the sort; label classes by
+    parity), the scheme sa_build.cu ships.  TINY=0 is the sparse-mode configuration (bag off)."""
+    from model_v5 import build_sa_v5
+
+    for name, text, sa in sa_golden:
+        if len(text) <= 1200:
+            assert build_sa_v5(text, M=4, T=8, TINY=3).tolist() == sa.tolist(), name
+    rng = np.random.default_rng(5)
+    cases = [b"a" * 300, b"ab" * 200 + b"b" + b"ab" * 100, b"abc" * 150, rng.integers(0, 2, 1500, dtype=np.uint8).tobytes()]
+    for per, nn, mut in ((50, 2500, 20), (7, 2000, 8), (13, 1500, 0)):
+        base = rng.integers(0, 256, per, dtype=np.uint8)
+        x = np.tile(base, nn // per + 1)[:nn].copy()
+        idx = rng.integers(0, nn, mut)
+        x[idx] = rng.integers(0, 256, mut)
+        cases.append(x.tobytes())
+    bagged = 0
+    for i, t in enumerate(cases):
+        exp = port.sa_build(t)
+        for (M, T, TINY) in ((4, 8, 3), (4, 16, 5), (8, 32, 9), (4, 8, 0)):
+            st = []
+            assert (build_sa_v5(t, M=M, T=T, TINY=TINY, shuffle_seed=i, stats=st) == exp).all(), (i, M, T, TINY)
+            bagged += sum(r[4] for r in st) if TINY else 0
+    assert bagged > 0  # the bag really was exercised
+
+
 def test_synth_shapes():
     from stringsearch_b200 import synth
 

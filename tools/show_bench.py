@@ -16,4 +16,4 @@ for path in sys.argv[1:]:
     if "-v" in sys.argv or len(d.get("rounds", [])) > 1:
         for r in d.get("rounds", []):
             print(f"    h={r['depth']:<6} L={r['live']:<11} S={r.get('sorted', r['live']):<11} hugeG={r['groups']:<8} bits={r['key_bits']} p={r['passes']} "
-                  f"ms={r['ms_total']:.2f} sort={r['ms_sort']:.2f}")
+                  f"ms={r['ms_total']:.2f} sort={r['ms_sort']:.2f} bag={r.get('bag', 0)}")
