@@ -8,11 +8,6 @@
 
 namespace gsa {
 
-struct RoundResult {
-  u32 live_out;    // suffixes still in non-singleton groups after the round
-  u32 bag_out;     // of which moved to the bag by this rebuild
-};
-
 // sa_build.cu
 size_t build_workspace_bytes(u32 n);
 int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t workspace_bytes, cudaStream_t st,

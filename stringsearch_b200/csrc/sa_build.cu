@@ -430,11 +430,8 @@ __device__ __forceinline__ u32 lazy_label(const KeyGen &g, const i32 *__restrict
 
 template <int THREADS, int IPT, int MIN_BLOCKS>
 __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_gather(const GatherArgs a) {
-  constexpr int WARPS = THREADS / 32;
   constexpr u32 CH = THREADS * IPT;
   __shared__ u32 shist[MAX_PASSES * RADIX];
-  __shared__ u32 s_wl[WARPS], s_ws[WARPS];
-  __shared__ u32 s_basel, s_bases;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int i = tid; i < a.npass * RADIX; i += THREADS) shist[i] = 0;
   __syncthreads();
@@ -516,21 +513,16 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_gather(const GatherArgs
       srt |= (so ? 1u : 0u) << k;
       if (ms) hist_add(shist, kx, so, a.npass);  // warp-uniform: rows of inert members skip it
     }
-    if (lane == 0) { s_wl[warp] = wl; s_ws[warp] = ws; }
-    __syncthreads();
-    if (tid == 0) {
-      u32 tl = 0, ts = 0;
-#pragma unroll
-      for (int x = 0; x < WARPS; ++x) {
-        const u32 cl = s_wl[x], cs = s_ws[x];
-        s_wl[x] = tl; s_ws[x] = ts;
-        tl += cl; ts += cs;
-      }
-      s_basel = tl ? atomicAdd(a.counter, tl) : 0u;
-      s_bases = ts ? atomicAdd(a.counter + 1, ts) : 0u;
+    // every warp reserves its own output ranges: the lists stay in text order within a warp's
+    // 32 * IPT candidates (which is what keeps the next round's reads coalesced), and no warp
+    // ever waits for another one's loads at a barrier
+    u32 bl = 0, bs = 0;
+    if (lane == 0) {
+      bl = wl ? atomicAdd(a.counter, wl) : 0u;
+      bs = ws ? atomicAdd(a.counter + 1, ws) : 0u;
     }
-    __syncthreads();
-    const u32 bl = s_basel + s_wl[warp], bs = s_bases + s_ws[warp];
+    bl = __shfl_sync(0xffffffffu, bl, 0);
+    bs = __shfl_sync(0xffffffffu, bs, 0);
 #pragma unroll
     for (int k = 0; k < IPT; ++k) {
       if ((w[k] & RANK_DEAD) == 0u) a.lst_out[bl + offl[k]] = sfx[k];
@@ -547,8 +539,8 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_gather(const GatherArgs
         }
       }
     }
-    __syncthreads();  // the shared counters are reused by the next chunk
   }
+  __syncthreads();
   for (int i = tid; i < a.npass * RADIX; i += THREADS)
     if (shist[i]) atomicAdd(&a.ghist[i], shist[i]);
 }
@@ -829,11 +821,11 @@ struct RebuildArgs {
   u32 tiny_max;        // groups of at most this many suffixes move to the bag (0: no bag)
   u64 *bag_desc;       // (first slot | size << 32) of every tiny group formed by this rebuild
   u32 *bag_desc_count;
-  ulonglong2 *status;  // [tiles] x = flag(2) | head+1 ; y = flag(2) | survivors(31) | moved to the bag(31)
   u32 *survivors;      // [1] k_tail_summary: number of elements that stay live after this round
   u32 *tile_tail;      // [tiles] k_tail_summary: first tail slot inside the tile (or NO_TAIL)
+  u32 *tile_head;      // [tiles] k_tail_summary: last head slot + 1 inside the tile (or 0)
   const u32 *next_tail;  // [tiles] k_tail_scan: first tail slot in any later tile
-  RoundResult *result;
+  const u32 *prev_head;  // [tiles] k_tail_scan: last head slot + 1 in any earlier tile
 };
 
 // Loads the IPT consecutive elements of this thread plus one neighbour on each side and
@@ -890,7 +882,7 @@ __global__ void __launch_bounds__(THREADS) k_tail_summary(const RebuildArgs a) {
   u64 kx[IPT + 2];
   u32 sx[IPT + 2];
   const u32 f = load_and_flag<IPT, ROUND0>(a, l0, kx, sx);
-  u32 v = NO_TAIL, surv = 0;
+  u32 v = NO_TAIL, surv = 0, hd = 0;  // first tail slot, survivors, last head slot + 1
   if (l0 < a.L) {
     const u32 nvalid = min((u32)IPT, a.L - l0);
     const u32 vm = (1u << nvalid) - 1u;
@@ -899,31 +891,63 @@ __global__ void __launch_bounds__(THREADS) k_tail_summary(const RebuildArgs a) {
       const u32 l = l0 + (u32)(__ffs(tails) - 1);
       v = ROUND0 ? l : (a.pos_in[l] & ~SLOT_HAS_RHO);
     }
+    const u32 heads = f & vm;
+    if (heads) {
+      const u32 l = l0 + (31u - (u32)__clz(heads));
+      hd = (ROUND0 ? l : (a.pos_in[l] & ~SLOT_HAS_RHO)) + 1u;
+    }
     surv = (u32)__popc(~(f & (f >> 1)) & vm);  // not (head and tail) = not unique yet
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+    hd = max(hd, __shfl_xor_sync(0xffffffffu, hd, o));
     surv += __shfl_xor_sync(0xffffffffu, surv, o);
   }
-  __shared__ u32 s_s[WARPS];
-  if (lane == 0) { s_w[warp] = v; s_s[warp] = surv; }
+  __shared__ u32 s_s[WARPS], s_h[WARPS];
+  if (lane == 0) { s_w[warp] = v; s_s[warp] = surv; s_h[warp] = hd; }
   __syncthreads();
   if (tid == 0) {
-    u32 m = NO_TAIL, t = 0;
+    u32 m = NO_TAIL, t = 0, h = 0;
 #pragma unroll
-    for (int w = 0; w < WARPS; ++w) { m = min(m, s_w[w]); t += s_s[w]; }
+    for (int w = 0; w < WARPS; ++w) { m = min(m, s_w[w]); t += s_s[w]; h = max(h, s_h[w]); }
     a.tile_tail[tile] = m;
+    a.tile_head[tile] = h;
     if (t) atomicAdd(a.survivors, t);
   }
 }
 
-// next_tail[t] = min over tiles t' > t of tile_tail[t'] (slots ascend, so the minimum is the nearest).
-__global__ void __launch_bounds__(1024) k_tail_scan(const u32 *__restrict__ tile_tail, u32 *__restrict__ next_tail, u32 tiles) {
+// next_tail[t] = min over tiles t' > t of tile_tail[t'] (slots ascend, so the minimum is the nearest);
+// if tile_head != null also prev_head[t] = max over tiles t' < t of tile_head[t'].
+// With these two per-tile carries the rebuild kernels need no look-back between their blocks.
+__global__ void __launch_bounds__(1024) k_tail_scan(const u32 *__restrict__ tile_tail, u32 *__restrict__ next_tail, u32 tiles,
+                                                    const u32 *__restrict__ tile_head, u32 *__restrict__ prev_head) {
   __shared__ u32 s_v[1024];
   const u32 t = threadIdx.x;
   const u32 per = (tiles + 1023u) / 1024u;
   const u32 lo = min(tiles, t * per), hi = min(tiles, lo + per);
+  if (tile_head != nullptr) {  // exclusive prefix-max over the chunk maxima, then inside the chunk
+    u32 m = 0;
+    for (u32 i = lo; i < hi; ++i) m = max(m, tile_head[i]);
+    s_v[t] = m;
+    __syncthreads();
+    u32 x = (t > 0) ? s_v[t - 1] : 0u;
+    __syncthreads();
+    s_v[t] = x;
+    __syncthreads();
+    for (u32 o = 1; o < 1024; o <<= 1) {
+      const u32 y = (t >= o) ? s_v[t - o] : 0u;
+      __syncthreads();
+      s_v[t] = max(s_v[t], y);
+      __syncthreads();
+    }
+    u32 carry = s_v[t];
+    for (u32 i = lo; i < hi; ++i) {
+      prev_head[i] = carry;
+      carry = max(carry, tile_head[i]);
+    }
+    __syncthreads();
+  }
   u32 m = NO_TAIL;
   for (u32 i = lo; i < hi; ++i) m = min(m, tile_tail[i]);
   s_v[t] = m;
@@ -957,8 +981,7 @@ template <int THREADS, int IPT, bool ROUND0, int MODE>
 __global__ void __launch_bounds__(THREADS, 2) k_rebuild(const RebuildArgs a) {
   constexpr int WARPS = THREADS / 32;
   constexpr int TILE = THREADS * IPT;
-  __shared__ u32 s_wh[WARPS], s_wc[WARPS], s_wg[WARPS], s_wt[WARPS];
-  __shared__ u32 s_pre[3];
+  __shared__ u32 s_wh[WARPS], s_wt[WARPS];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // Tiles are taken in blockIdx order: the look-back only ever waits on lower-numbered
   // blocks, which the hardware dispatches first.
@@ -995,92 +1018,38 @@ __global__ void __launch_bounds__(THREADS, 2) k_rebuild(const RebuildArgs a) {
   if (l0 < L) nvalid = min((u32)IPT, L - l0);
 
   // ---- thread aggregates ------------------------------------------------------------------
-  u32 th = 0, tc = 0, tg = 0;  // last flagged slot + 1, survivors, surviving group heads
-  u32 tt = NO_TAIL;            // first tail slot
+  u32 th = 0;        // last flagged slot + 1
+  u32 tt = NO_TAIL;  // first tail slot
 #pragma unroll
   for (int j = IPT - 1; j >= 0; --j)
     if ((u32)j < nvalid && ((f >> (j + 1)) & 1u)) tt = px[j];
 #pragma unroll
-  for (int j = 0; j < IPT; ++j) {
-    if ((u32)j < nvalid) {
-      const bool fj = (f >> j) & 1u, fn = (f >> (j + 1)) & 1u;
-      if (fj) th = px[j] + 1u;
-      if (!(fj && fn)) ++tc;
-      if (fj && !fn) ++tg;
-    }
-  }
-  // ---- block scans: forward (max, sum, sum) and backward (min) ---------------------------------
-  u32 ih = th, ic = tc, ig = tg, it = tt;
+  for (int j = 0; j < IPT; ++j)
+    if ((u32)j < nvalid && ((f >> j) & 1u)) th = px[j] + 1u;
+  // ---- block scans: forward max (head) and backward min (tail); the carries across tiles were
+  // prepared by k_tail_summary + k_tail_scan, so no block waits for another one --------------------
+  u32 ih = th, it = tt;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
     const u32 yh = __shfl_up_sync(0xffffffffu, ih, o);
-    const u32 yc = __shfl_up_sync(0xffffffffu, ic, o);
-    const u32 yg = __shfl_up_sync(0xffffffffu, ig, o);
     const u32 yt = __shfl_down_sync(0xffffffffu, it, o);
-    if (lane >= o) { ih = max(ih, yh); ic += yc; ig += yg; }
+    if (lane >= o) ih = max(ih, yh);
     if (lane + o < 32) it = min(it, yt);
   }
-  if (lane == 31) { s_wh[warp] = ih; s_wc[warp] = ic; s_wg[warp] = ig; }
+  if (lane == 31) s_wh[warp] = ih;
   if (lane == 0) s_wt[warp] = it;
-  u32 eh = __shfl_up_sync(0xffffffffu, ih, 1), ec = ic - tc, eg = ig - tg;
+  u32 eh = __shfl_up_sync(0xffffffffu, ih, 1);
   u32 et = __shfl_down_sync(0xffffffffu, it, 1);
   if (lane == 0) eh = 0;
   if (lane == 31) et = NO_TAIL;
   __syncthreads();
-  u32 bh = 0, bc = 0, bg = 0;  // block totals (all warps)
-  {
-    u32 ph = 0, pc = 0, pg = 0;
 #pragma unroll
-    for (int w = 0; w < WARPS; ++w) {
-      if (w == warp) { ph = bh; pc = bc; pg = bg; }
-      bh = max(bh, s_wh[w]); bc += s_wc[w]; bg += s_wg[w];
-      if (w > warp) et = min(et, s_wt[w]);
-    }
-    eh = max(eh, ph); ec += pc; eg += pg;
+  for (int w = 0; w < WARPS; ++w) {
+    if (w < warp) eh = max(eh, s_wh[w]);
+    if (w > warp) et = min(et, s_wt[w]);
   }
+  eh = max(eh, a.prev_head[tile]);  // head slot + 1 of the group that reaches into this thread's elements
   et = min(et, a.next_tail[tile]);  // first tail slot after this thread's elements
-
-  // ---- tile prefix by decoupled look-back (warp 0, 32 predecessors per round trip) ----------
-  if (warp == 0) {
-    u32 xh = 0, xc = 0, xg = 0;  // exclusive prefix over preceding tiles
-    if (tile == 0) {
-      if (lane == 0) st_status(a.status, ST_PRE | bh, ST_PRE | ((u64)bc << 31) | bg);
-    } else {
-      if (lane == 0) st_status(a.status + tile, ST_AGG | bh, ST_AGG | ((u64)bc << 31) | bg);
-      i64 look = (i64)tile - 1 - lane;  // lane 0 inspects the nearest predecessor
-      for (;;) {
-        ulonglong2 sv = make_ulonglong2(ST_PRE, ST_PRE);  // virtual tiles before tile 0: identity prefix
-        if (look >= 0) {
-          do { sv = ld_status(a.status + look); } while ((sv.x & ST_FLAG) == 0 || (sv.x & ST_FLAG) != (sv.y & ST_FLAG));
-        }
-        const u32 pre = __ballot_sync(0xffffffffu, (sv.x & ST_FLAG) == ST_PRE);
-        const int first = pre ? (__ffs(pre) - 1) : 32;  // nearest tile holding an inclusive prefix
-        u32 vh = 0, vc = 0, vg = 0;
-        if (lane <= first) {
-          vh = (u32)(sv.x & 0xffffffffull);
-          vc = (u32)((sv.y >> 31) & 0x7fffffffull);
-          vg = (u32)(sv.y & 0x7fffffffull);
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          vh = max(vh, __shfl_xor_sync(0xffffffffu, vh, o));
-          vc += __shfl_xor_sync(0xffffffffu, vc, o);
-          vg += __shfl_xor_sync(0xffffffffu, vg, o);
-        }
-        xh = max(xh, vh); xc += vc; xg += vg;
-        if (pre) break;
-        look -= 32;
-      }
-      if (lane == 0) st_status(a.status + tile, ST_PRE | max(xh, bh), ST_PRE | ((u64)(xc + bc) << 31) | (xg + bg));
-    }
-    if (lane == 0) {
-      s_pre[0] = xh; s_pre[1] = xc; s_pre[2] = xg;
-      if ((u64)(tile + 1) * TILE >= L) {  // last tile: totals of the round
-        a.result->live_out = xc + bc;
-      }
-    }
-  }
-  __syncthreads();
 
   // ---- emit ------------------------------------------------------------------------------------
   u32 tl[IPT];  // tail slot of every element
@@ -1092,8 +1061,29 @@ __global__ void __launch_bounds__(THREADS, 2) k_rebuild(const RebuildArgs a) {
       tl[j] = cur;
     }
   }
-  u32 head = max(s_pre[0], eh);  // head slot + 1
-  u32 c = s_pre[1] + ec;
+  // tiny groups headed here: one descriptor each, reserved with one atomic per warp
+  u32 dbase = 0;
+  if (a.tiny_max) {
+    u32 nd = 0, head = eh;
+#pragma unroll
+    for (int j = 0; j < IPT; ++j) {
+      if ((u32)j < nvalid && ((f >> j) & 1u)) {
+        head = px[j] + 1u;
+        const u32 size = tl[j] + 2u - head;
+        nd += (size > 1u && size <= a.tiny_max) ? 1u : 0u;
+      }
+    }
+    u32 inc = nd;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const u32 y = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += y;
+    }
+    u32 wb = 0;
+    if (lane == 31 && inc) wb = atomicAdd(a.bag_desc_count, inc);
+    dbase = __shfl_sync(0xffffffffu, wb, 31) + inc - nd;
+  }
+  u32 head = eh;  // head slot + 1
 #pragma unroll
   for (int j = 0; j < IPT; ++j) {
     if ((u32)j < nvalid) {
@@ -1117,7 +1107,7 @@ __global__ void __launch_bounds__(THREADS, 2) k_rebuild(const RebuildArgs a) {
         if (tiny) a.SA[px[j]] = (i32)sx[j + 1];  // provisional order: the bag is backed by SA
         if ((f >> j) & 1u) {  // group head: publish the group's slot range
           if (tiny) {
-            a.bag_desc[atomicAdd(a.bag_desc_count, 1u)] = (u64)(s1 - 1u) | ((u64)size << 32);
+            a.bag_desc[dbase++] = (u64)(s1 - 1u) | ((u64)size << 32);
           } else {
             a.G[lab] = (u64)(s1 - 1u) | ((u64)(e1 - 1u) << 32);
             if (!keep && is_huge_label(lab)) {
@@ -1128,7 +1118,6 @@ __global__ void __launch_bounds__(THREADS, 2) k_rebuild(const RebuildArgs a) {
           }
         }
         if (MODE == RB_SPARSE) a.SA[px[j]] = (i32)sx[j + 1];
-        ++c;
       }
     }
   }
@@ -1146,14 +1135,41 @@ __global__ void __launch_bounds__(THREADS, 2) k_rebuild(const RebuildArgs a) {
 __global__ void __launch_bounds__(256) k_bag_append(const u64 *__restrict__ desc, const u32 *__restrict__ desc_count,
                                                     const i32 *__restrict__ SA, u32 *__restrict__ bag_sufx,
                                                     u32 *__restrict__ bag_pos, u32 *__restrict__ bag_count) {
+  // a warp expands 32 descriptors together: one reservation, then 32 entries per step, each lane
+  // finding the descriptor of its entry by binary search over the warp's running sizes
   const u32 q = blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= *desc_count) return;
-  const u64 d = desc[q];
+  const u32 lane = threadIdx.x & 31u;
+  const u32 nd = *desc_count;
+  if (q - lane >= nd) return;  // whole warp
+  const u64 d = (q < nd) ? desc[q] : 0ull;
   const u32 s = (u32)d, size = (u32)(d >> 32);
-  const u32 base = atomicAdd(bag_count, size);
-  for (u32 j = 0; j < size; ++j) {
-    bag_sufx[base + j] = (u32)SA[s + j];
-    bag_pos[base + j] = (s + j) | (j == 0 ? BAG_HEAD : 0u);
+  u32 inc = size;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const u32 y = __shfl_up_sync(0xffffffffu, inc, o);
+    if ((int)lane >= o) inc += y;
+  }
+  const u32 total = __shfl_sync(0xffffffffu, inc, 31);
+  u32 base = 0;
+  if (lane == 0) base = atomicAdd(bag_count, total);
+  base = __shfl_sync(0xffffffffu, base, 0);
+  for (u32 e0 = 0; e0 < total; e0 += 32u) {
+    const u32 e = e0 + lane;
+    // first descriptor whose inclusive running size exceeds e
+    u32 lo = 0;
+#pragma unroll
+    for (int step = 16; step > 0; step >>= 1) {
+      const u32 probe = __shfl_sync(0xffffffffu, inc, (int)(lo + step - 1u));
+      if (probe <= e) lo += (u32)step;
+    }
+    const u32 ds = __shfl_sync(0xffffffffu, s, (int)lo);
+    const u32 dend = __shfl_sync(0xffffffffu, inc, (int)lo);
+    const u32 dsize = __shfl_sync(0xffffffffu, size, (int)lo);
+    if (e < total) {
+      const u32 j = e - (dend - dsize);
+      bag_sufx[base + e] = (u32)SA[ds + j];
+      bag_pos[base + e] = (ds + j) | (j == 0 ? BAG_HEAD : 0u);
+    }
   }
 }
 
@@ -1172,8 +1188,8 @@ __global__ void __launch_bounds__(256) k_bag_gather(const u32 *__restrict__ bag_
   }
 }
 
-constexpr int BAG_TILE = 960;
-constexpr int BAG_THREADS = BAG_TILE + (int)TINY_MAX;  // 1024
+constexpr int BAG_THREADS = 512;
+constexpr int BAG_TILE = BAG_THREADS - (int)TINY_MAX;
 
 struct BagArgs {
   const u32 *sufx_in, *pos_in, *r2;
@@ -1183,25 +1199,40 @@ struct BagArgs {
   i32 *SA;
 };
 
-__global__ void __launch_bounds__(BAG_THREADS, 1) k_bag_refine(const BagArgs a) {
-  __shared__ u32 s_sfx[BAG_THREADS], s_pos[BAG_THREADS], s_r2[BAG_THREADS];
+__global__ void __launch_bounds__(BAG_THREADS) k_bag_refine(const BagArgs a) {
+  constexpr u32 NW = BAG_THREADS / 32;
+  static_assert(NW <= 32, "warp totals are scanned by one warp");
+  __shared__ u32 s_sfx[BAG_THREADS], s_r2[BAG_THREADS];
   __shared__ u32 s_slot[BAG_THREADS];  // new slot, bit 31 = survives (its run has more than one member)
   __shared__ u32 s_excl[BAG_THREADS];  // survivors before this entry (block order)
-  __shared__ u32 s_warp[BAG_THREADS / 32];
+  __shared__ u32 s_gs[BAG_THREADS];    // slot of the entry (first slot of the group at a head)
+  __shared__ u32 s_headm[NW];          // per warp: which entries start a group
+  __shared__ u32 s_warp[32];
   __shared__ u32 s_base;
-  const u32 tid = threadIdx.x;
+  const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
   const u32 l = blockIdx.x * (u32)BAG_TILE + tid;
   const bool have = l < a.nb;
+  const u32 pos = have ? a.pos_in[l] : BAG_HEAD;  // past the end: looks like the start of another group
   s_sfx[tid] = have ? a.sufx_in[l] : 0u;
-  s_pos[tid] = have ? a.pos_in[l] : BAG_HEAD;  // past the end: looks like the start of another group
   s_r2[tid] = have ? a.r2[l] : 0u;
+  s_gs[tid] = pos & ~BAG_HEAD;
+  const u32 hm = __ballot_sync(0xffffffffu, (pos & BAG_HEAD) != 0u);
+  if (lane == 0) s_headm[warp] = hm;
   __syncthreads();
   // my group: [g0, g1) in block coordinates; it belongs to this block iff its head is below BAG_TILE
-  u32 g0 = tid;
-  while (!(s_pos[g0] & BAG_HEAD) && g0 > 0) --g0;
-  const bool head_seen = (s_pos[g0] & BAG_HEAD) != 0u;  // false: the head is in the previous block
-  u32 g1 = tid + 1;
-  while (g1 < (u32)BAG_THREADS && !(s_pos[g1] & BAG_HEAD)) ++g1;
+  u32 g0 = 0, g1 = (u32)BAG_THREADS;
+  bool head_seen;
+  {
+    u32 m = s_headm[warp] & (0xffffffffu >> (31u - lane));  // heads at or before me
+    u32 w = warp;
+    while (m == 0u && w > 0u) m = s_headm[--w];
+    head_seen = m != 0u;  // false: the head is in the previous block
+    if (head_seen) g0 = w * 32u + 31u - (u32)__clz(m);
+    m = (lane == 31u) ? 0u : (s_headm[warp] & (0xffffffffu << (lane + 1u)));  // heads after me
+    w = warp;
+    while (m == 0u && w + 1u < NW) m = s_headm[++w];
+    if (m != 0u) g1 = w * 32u + (u32)__ffs(m) - 1u;
+  }
   const bool mine = have && head_seen && g0 < (u32)BAG_TILE;
   u32 less = 0, eq = 0, eq_before = 0;
   const u32 my = s_r2[tid];
@@ -1213,7 +1244,7 @@ __global__ void __launch_bounds__(BAG_THREADS, 1) k_bag_refine(const BagArgs a) 
       eq_before += (v == my && m < tid) ? 1u : 0u;
     }
   }
-  const u32 gs = s_pos[g0] & ~BAG_HEAD;           // first slot of the old group
+  const u32 gs = s_gs[g0];                        // first slot of the old group
   const u32 s1 = gs + less, slot = s1 + eq_before;  // first slot of my run, my own slot
   const bool surv = mine && eq > 1u;
   s_slot[tid] = mine ? (slot | (surv ? BAG_HEAD : 0u)) : 0u;
@@ -1222,8 +1253,8 @@ __global__ void __launch_bounds__(BAG_THREADS, 1) k_bag_refine(const BagArgs a) 
   const u32 bal = __ballot_sync(0xffffffffu, surv);
   if ((tid & 31u) == 0u) s_warp[tid >> 5] = (u32)__popc(bal);
   __syncthreads();
-  if (tid < 32u) {  // exclusive scan of the 32 warp totals
-    const u32 v = s_warp[tid];
+  if (tid < 32u) {  // exclusive scan of the warp totals
+    const u32 v = (tid < NW) ? s_warp[tid] : 0u;
     u32 inc = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -1298,10 +1329,8 @@ struct Layout {
   u32 *skip_mask;  // [1]
   u32 *live_counter;  // [1] k_gather
   u32 *survivors;     // [1] k_tail_summary
-  RoundResult *result;
   u32 *pass_status; size_t pass_status_words;  // counter at word 0 (256-word header), then [tiles][256]
-  ulonglong2 *rb_status;                       // one 16-byte descriptor per rebuild tile
-  u32 *tile_tail, *next_tail;                  // per rebuild tile
+  u32 *tile_tail, *next_tail, *tile_head, *prev_head;  // per rebuild tile
   u32 *bag_sufx[2], *bag_pos[2];               // the bag: (suffix, slot | BAG_HEAD), group after group
   u32 *bag_count;                              // [0], [1] entries of the two bag buffers, [2] descriptors
   size_t total;
@@ -1338,14 +1367,14 @@ Layout make_layout(char *base, u32 n) {
   y.skip_mask = c.take<u32>(64);
   y.live_counter = c.take<u32>(64);
   y.survivors = c.take<u32>(64);
-  y.result = c.take<RoundResult>(16);
   const size_t ptiles = div_up(N, 3072);  // smallest tile of the pass configurations
   y.pass_status_words = 256 + ptiles * RADIX;
   y.pass_status = c.take<u32>(y.pass_status_words);
   const size_t rtiles = div_up(N, RB_TILE);
-  y.rb_status = c.take<ulonglong2>(rtiles + 1);
   y.tile_tail = c.take<u32>(rtiles + 1);
   y.next_tail = c.take<u32>(rtiles + 1);
+  y.tile_head = c.take<u32>(rtiles + 1);
+  y.prev_head = c.take<u32>(rtiles + 1);
   y.slot_status = c.take<u64>(rtiles + 1);
   y.tile_rtail = c.take<u32>(rtiles + 1);
   y.next_rtail = c.take<u32>(rtiles + 1);
@@ -1605,7 +1634,6 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
   GSA_TRY(cudaMemsetAsync(y.bag_count, 0, 4 * sizeof(u32), st));
   auto launch_rebuild = [&](bool round0, u32 L, int kv, bool may_finish, u32 *survivors_out) -> int {
     const u32 tiles = (u32)div_up(L, RB_TILE);
-    GSA_TRY(cudaMemsetAsync(y.rb_status, 0, (size_t)tiles * sizeof(ulonglong2), st));
     GSA_TRY(cudaMemsetAsync(y.survivors, 0, sizeof(u32), st));
     RebuildArgs r;
     r.keys = y.keys[kv]; r.sufx = y.vals[kv];
@@ -1616,10 +1644,9 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
     r.rank = y.rank; r.SA = d_SA;
     r.G = y.G; r.hlist = y.hlist[hcur]; r.hcount = y.hcount + hcur; r.rep = y.rep;
     r.hkt = HugeKeyTable{y.hkt_keys, y.hkt_labels, y.hkt_cap - 1};
-    r.status = y.rb_status;
     r.survivors = y.survivors;
     r.tile_tail = y.tile_tail; r.next_tail = y.next_tail;
-    r.result = y.result;
+    r.tile_head = y.tile_head; r.prev_head = y.prev_head;
     r.tiny_max = sparse ? 0u : tiny_conf;
     r.bag_desc = y.keys[kv ^ 1];  // the other half of the sort's double buffer is free until the next walk
     r.bag_desc_count = y.bag_count + 2;
@@ -1627,7 +1654,7 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
     if (round0) k_tail_summary<RB_THREADS, RB_IPT, true><<<tiles, RB_THREADS, 0, st>>>(r);
     else k_tail_summary<RB_THREADS, RB_IPT, false><<<tiles, RB_THREADS, 0, st>>>(r);
     KLAUNCH_CHECK();
-    k_tail_scan<<<1, 1024, 0, st>>>(y.tile_tail, y.next_tail, tiles);
+    k_tail_scan<<<1, 1024, 0, st>>>(y.tile_tail, y.next_tail, tiles, y.tile_head, y.prev_head);
     KLAUNCH_CHECK();
     u32 surv = 0, bag_left = 0;
     GSA_TRY(cudaMemcpyAsync(&surv, y.survivors, sizeof(u32), cudaMemcpyDeviceToHost, st));
@@ -1783,7 +1810,7 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
       GSA_TRY(cudaMemsetAsync(y.gupd_count, 0, sizeof(u32), st));
       k_run_summary<RB_THREADS, RB_IPT><<<tiles, RB_THREADS, 0, st>>>(sa);
       KLAUNCH_CHECK();
-      k_tail_scan<<<1, 1024, 0, st>>>(y.tile_rtail, y.next_rtail, tiles);
+      k_tail_scan<<<1, 1024, 0, st>>>(y.tile_rtail, y.next_rtail, tiles, nullptr, nullptr);
       KLAUNCH_CHECK();
       k_slots<RB_THREADS, RB_IPT><<<tiles, RB_THREADS, 0, st>>>(sa);
       KLAUNCH_CHECK();
