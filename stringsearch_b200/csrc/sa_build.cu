@@ -234,7 +234,7 @@ __device__ __forceinline__ bool is_huge_label(u32 lab) { return (lab & (HUGE_M -
 //   other even label   : medium, sorted through the text-order path every round
 //   odd label          : tiny, lives in the bag; always the canonical label of its slot range
 // (tiny_max == 0 switches the tiny class off: sparse mode, which keeps no label for most suffixes.)
-constexpr u32 TINY_MAX = 64;
+constexpr u32 TINY_MAX = 128;
 constexpr u32 BAG_HEAD = 0x80000000u;  // bag entry: first member of its group
 
 __device__ __forceinline__ u32 tiny_label(u32 s) { return (s & 1u) ? s + 2u : s + 1u; }  // first odd label in [s+1, ..]
@@ -315,7 +315,8 @@ __global__ void __launch_bounds__(256) k_rank_huge0(const KeyGen g, const HugeKe
 // readers of this round, and rebuild the list of huge groups.
 __global__ void __launch_bounds__(256) k_huge_prepare(const u32 *__restrict__ hin, u32 cnt, u64 *__restrict__ G,
                                                       u64 *__restrict__ state, u32 *__restrict__ rep, u32 round,
-                                                      u32 tiny_max, u32 *__restrict__ hout, u32 *__restrict__ hout_count) {
+                                                      u32 tiny_max, u32 *__restrict__ hout, u32 *__restrict__ hout_count,
+                                                      u32 *__restrict__ verdicts) {
   const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= cnt) return;
   const u32 lab = hin[j];
@@ -324,7 +325,7 @@ __global__ void __launch_bounds__(256) k_huge_prepare(const u32 *__restrict__ hi
   const i64 size = ge - gs + 1;
   const u64 tag = (u64)round << 32;
   if (size <= 0) return;  // every member left the inert block
-  if (size == 1) { state[lab / HUGE_M] = tag | STATE_FINAL | (u32)(gs + 1); return; }
+  if (size == 1) { state[lab / HUGE_M] = tag | STATE_FINAL | (u32)(gs + 1); *verdicts = 1u; return; }
   if (size < (i64)HUGE_T || !((i64)lab >= gs + 1 && (i64)lab <= ge + 1)) {
     // new huge label inside the range, or the label of the class the group has shrunk to (if tiny,
     // its members -- still in the text-order list -- are all sorted this round and the rebuild
@@ -332,6 +333,7 @@ __global__ void __launch_bounds__(256) k_huge_prepare(const u32 *__restrict__ hi
     const u32 nl = pick_label((u32)gs, (u32)ge, 0u, tiny_max);
     G[nl] = g;
     state[lab / HUGE_M] = tag | nl;
+    *verdicts = 1u;  // readers must consult STATE this round
     if (is_huge_label(nl)) {
       for (u32 x = 0; x < HUGE_REPS; ++x) rep[(nl / HUGE_M) * HUGE_REPS + x] = rep[(lab / HUGE_M) * HUGE_REPS + x];
       hout[atomicAdd(hout_count, 1u)] = nl;
@@ -393,6 +395,7 @@ struct GatherArgs {
   int filter;         // leave inert members of huge groups out of the sort
   u32 tiny_max;       // > 0: suffixes with an odd label live in the bag and are dropped from the list
   const u64 *state;   // [n / HUGE_M + 2] verdicts of k_huge_prepare, tagged with the round
+  const u32 *verdicts;  // [1] != 0: some huge group got a verdict this round (else STATE need not be read)
   const u64 *rho;     // [n / HUGE_M + 2] round << 32 | rho*  (k_huge_rho)
   u32 *rep;           // [n / HUGE_M + 2][HUGE_REPS] members of every huge group, refreshed from the inert ones
   u64 *keys_out;
@@ -436,6 +439,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_gather(const GatherArgs
   for (int i = tid; i < a.npass * RADIX; i += THREADS) shist[i] = 0;
   __syncthreads();
   const u32 lt = lanemask_lt();
+  const bool anyv = __ldg(a.verdicts) != 0u;
   const u32 nchunks = (a.Lin + CH - 1) / CH;
   for (u32 chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
     // warp w owns the contiguous sub-chunk [w*32*IPT, (w+1)*32*IPT); row k = 32 consecutive candidates
@@ -462,6 +466,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_gather(const GatherArgs
     // loads of all IPT rows are issued together, three times: STATE of the suffix, STATE of
     // suffix + h, rho* of the (resolved) group.
     u64 tb[IPT];
+    if (anyv) {  // (warp-uniform) in most rounds no huge group changes its state
 #pragma unroll
     for (int k = 0; k < IPT; ++k) tb[k] = needs_state(w[k]) ? __ldg(a.state + (w[k] / HUGE_M)) : 0ull;
 #pragma unroll
@@ -485,6 +490,10 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_gather(const GatherArgs
     for (int k = 0; k < IPT; ++k) {
       bool fin;
       if (!(w[k] & RANK_DEAD) && r2[k] != 0u) r2[k] = resolve_with(r2[k], tb[k], a.round, &fin);
+    }
+    } else {
+#pragma unroll
+      for (int k = 0; k < IPT; ++k) r2[k] &= RANK_MASK;  // a finalised suffix: its slot + 1
     }
 #pragma unroll
     for (int k = 0; k < IPT; ++k)
@@ -525,7 +534,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_gather(const GatherArgs
     bs = __shfl_sync(0xffffffffu, bs, 0);
 #pragma unroll
     for (int k = 0; k < IPT; ++k) {
-      if ((w[k] & RANK_DEAD) == 0u) a.lst_out[bl + offl[k]] = sfx[k];
+      if (a.lst_out != nullptr && (w[k] & RANK_DEAD) == 0u) a.lst_out[bl + offl[k]] = sfx[k];
       if ((srt >> k) & 1u) {
         const u32 o = bs + offs[k];
         a.keys_out[o] = ((u64)w[k] << a.lab_bits) | r2[k];
@@ -1174,15 +1183,17 @@ __global__ void __launch_bounds__(256) k_bag_append(const u64 *__restrict__ desc
 }
 
 __global__ void __launch_bounds__(256) k_bag_gather(const u32 *__restrict__ bag_sufx, u32 nb, const u32 *__restrict__ rank,
-                                                    const u64 *__restrict__ state, u32 round, u64 h, u32 n,
-                                                    u32 *__restrict__ r2out) {
+                                                    const u64 *__restrict__ state, const u32 *__restrict__ verdicts,
+                                                    u32 round, u64 h, u32 n, u32 *__restrict__ r2out) {
   const u32 stride = gridDim.x * blockDim.x;
+  const bool anyv = __ldg(verdicts) != 0u;
   for (u32 l = blockIdx.x * blockDim.x + threadIdx.x; l < nb; l += stride) {
     const u64 t = (u64)__ldg(bag_sufx + l) + h;
     u32 r2 = 0;
     if (t < n) {
       bool fin;
-      r2 = resolve_label(__ldcg(rank + t), state, round, &fin);
+      const u32 w = __ldcg(rank + t);
+      r2 = anyv ? resolve_label(w, state, round, &fin) : (w & RANK_MASK);
     }
     r2out[l] = r2;
   }
@@ -1619,7 +1630,11 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
   GSA_TRY_RC(run_passes(y, n, npass0, 0, &gen, st, stats, timer, &cur, &passes));
   GSA_TRY(cudaEventRecord(ev[2], st));
 
-  const u32 lab_bits = bits_for(n);  // labels are 1..n
+  // key = label(i) << 32 | label(i + h).  The label half starts on a digit boundary on purpose:
+  // huge labels are multiples of 256, so in a round that sorts only members of huge groups the
+  // digit holding their low byte is constant and its pass is skipped (as are the digits above
+  // bits_for(n) in both halves).
+  const u32 lab_bits = 32;
   bool sparse = false;
   int hcur = 0;  // hlist[hcur] / hcount[hcur]: huge groups entering the next round
   GSA_TRY(cudaMemsetAsync(y.state, 0, ((size_t)n / HUGE_M + 2) * sizeof(u64), st));
@@ -1629,7 +1644,8 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
   // tail summaries + survivor count, then the rebuild proper.  *survivors_out is known before the
   // rebuild is launched, which lets the last round skip its rank writes.
   // The bag is off in sparse mode (most suffixes then carry no label at all).
-  const u32 tiny_conf = getenv("GSA_NO_BAG") ? 0u : TINY_MAX;
+  u32 tiny_conf = getenv("GSA_NO_BAG") ? 0u : TINY_MAX;
+  if (const char *e = getenv("GSA_TINY_MAX")) tiny_conf = std::min<u32>(TINY_MAX, (u32)atoi(e));
   int bcur = 0;  // bag buffer the rebuild of the current round appends to (= input of the next round)
   GSA_TRY(cudaMemsetAsync(y.bag_count, 0, 4 * sizeof(u32), st));
   auto launch_rebuild = [&](bool round0, u32 L, int kv, bool may_finish, u32 *survivors_out) -> int {
@@ -1731,8 +1747,9 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
     GSA_TRY(cudaStreamSynchronize(st));
     if (hc > y.hcap / 2) { set_error("huge-group list overflow", __FILE__, __LINE__); return GSA_ECUDA; }
     GSA_TRY(cudaMemsetAsync(y.hcount + (hcur ^ 1), 0, sizeof(u32), st));
+    GSA_TRY(cudaMemsetAsync(y.hcount + 2, 0, sizeof(u32), st));
     if (hc) {
-      k_huge_prepare<<<(u32)div_up(hc, 256), 256, 0, st>>>(y.hlist[hcur], hc, y.G, y.state, y.rep, round, tiny_max, y.hlist[hcur ^ 1], y.hcount + (hcur ^ 1));
+      k_huge_prepare<<<(u32)div_up(hc, 256), 256, 0, st>>>(y.hlist[hcur], hc, y.G, y.state, y.rep, round, tiny_max, y.hlist[hcur ^ 1], y.hcount + (hcur ^ 1), y.hcount + 2);
       KLAUNCH_CHECK();
       if (stats) stats->kernel_launches++;
     }
@@ -1750,8 +1767,11 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
     g.Lin = Lcand; g.rank = y.rank; g.SA = d_SA; g.n = n; g.h = h; g.lab_bits = lab_bits;
     g.npass = sparse ? 0 : npass;  // sparse: keys are completed by k_lazy_fill, histogram afterwards
     g.tiny_max = tiny_max;
-    g.round = round; g.filter = filter ? 1 : 0; g.state = y.state; g.rho = y.rho; g.rep = y.rep;
-    g.keys_out = y.keys[0]; g.vals_out = y.vals[0]; g.lst_out = y.lst[lcur ^ 1];
+    g.round = round; g.filter = filter ? 1 : 0; g.state = y.state; g.verdicts = y.hcount + 2; g.rho = y.rho; g.rep = y.rep;
+    // While most of the text is live the candidate list is not worth its 8 bytes per suffix:
+    // the next round simply walks all text positions again.
+    const bool write_list = (u64)live * 2 < n || sparse;
+    g.keys_out = y.keys[0]; g.vals_out = y.vals[0]; g.lst_out = write_list ? y.lst[lcur ^ 1] : nullptr;
     g.counter = y.live_counter; g.ghist = y.ghist;
     g.sa0 = sparse ? d_SA : nullptr;
     g.gen = gen;
@@ -1769,7 +1789,7 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
     GSA_TRY(cudaMemsetAsync(y.bag_count + bcur, 0, sizeof(u32), st));
     if (nbag) {
       const u32 bb = (u32)std::min<u64>((u64)sms * 8, div_up(nbag, 256));
-      k_bag_gather<<<bb, 256, 0, st>>>(y.bag_sufx[bin], nbag, y.rank, y.state, round, h, n, y.slots);
+      k_bag_gather<<<bb, 256, 0, st>>>(y.bag_sufx[bin], nbag, y.rank, y.state, y.hcount + 2, round, h, n, y.slots);
       KLAUNCH_CHECK();
       BagArgs ba;
       ba.sufx_in = y.bag_sufx[bin]; ba.pos_in = y.bag_pos[bin]; ba.r2 = y.slots; ba.nb = nbag;
@@ -1829,9 +1849,11 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
     log_round(h, Llive, S, hc, kb, passes, nbag);
     live = (Llive - S) + survivors;  // inert members + non-unique sorted ones (some of them now in the bag)
     nbag = nbag_next;
-    lcur ^= 1;
-    Lcand = Llive;
-    ident = false;
+    if (write_list) {
+      lcur ^= 1;
+      Lcand = Llive;
+      ident = false;
+    }
     if (round > 64) { set_error("prefix doubling did not converge", __FILE__, __LINE__); return GSA_ECUDA; }
   }
   GSA_TRY(cudaEventRecord(ev_all1, st));
