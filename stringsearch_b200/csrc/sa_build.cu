@@ -585,29 +585,13 @@ __global__ void __launch_bounds__(THREADS) k_hist_keys(const u64 *__restrict__ k
 // live member except the inert ones.  With G[label] = (gs, ge) and, for a huge group, its rho*:
 //   second key half < rho* (or no rho*): slot = gs + (index inside the run)
 //   second key half > rho*             : slot = ge - (elements behind it in the run)
-// Index inside the run needs the run head (forward max-scan, decoupled look-back), elements
-// behind it the run tail (backward min-scan; k_run_summary + k_tail_scan give "first run tail
-// after tile t").  The two ends of the inert block move inwards past the sorted members:
+// Index inside the run needs the run head (forward max-scan), elements behind it the run tail
+// (backward min-scan); k_run_summary + k_tail_scan prepare both carries across tiles ("last run
+// head before tile t", "first run tail after tile t"), so no block waits for another one.  The two ends of the inert block move inwards past the sorted members:
 // the last "<" element and the first ">" element of a run record the new ends in a small
 // update list, applied by k_apply_g after this kernel (G is read here, so it is not written).
 // Bit 31 of the slot word tells the rebuild that the run has an inert block.
 // ------------------------------------------------------------------------------------
-constexpr u64 ST_AGG = 1ull << 62;
-constexpr u64 ST_PRE = 2ull << 62;
-constexpr u64 ST_FLAG = 3ull << 62;
-
-// One 16-byte, 16-byte-aligned access per tile descriptor (a single memory transaction on
-// the hardware).  Both halves carry the state flag, so a torn read -- should one ever
-// happen -- is seen as "flags differ" and simply retried.
-__device__ __forceinline__ ulonglong2 ld_status(const ulonglong2 *p) {
-  ulonglong2 v;
-  asm volatile("ld.volatile.global.v2.u64 {%0,%1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_status(ulonglong2 *p, u64 x, u64 y) {
-  asm volatile("st.volatile.global.v2.u64 [%0], {%1,%2};" ::"l"(p), "l"(x), "l"(y) : "memory");
-}
-
 struct SlotArgs {
   const u64 *keys;
   u32 S;
@@ -617,9 +601,10 @@ struct SlotArgs {
   u32 round;
   int filter;
   u32 *slots;
-  u64 *status;          // [tiles] flag(2) | run head index + 1
   u32 *tile_rtail;      // [tiles] k_run_summary: first run-tail index inside the tile
-  const u32 *next_rtail;
+  u32 *tile_rhead;      // [tiles] k_run_summary: last run-head index + 1 inside the tile (or 0)
+  const u32 *next_rtail;  // [tiles] k_tail_scan: first run-tail index in any later tile
+  const u32 *prev_rhead;  // [tiles] k_tail_scan: last run-head index + 1 in any earlier tile
   u32 *gupd;            // triples (label, 0 = first slot / 1 = last slot, value)
   u32 *gupd_count;
 };
@@ -628,30 +613,37 @@ constexpr u32 SLOT_HAS_RHO = 0x80000000u;
 template <int THREADS, int IPT>
 __global__ void __launch_bounds__(THREADS) k_run_summary(const SlotArgs a) {
   constexpr int WARPS = THREADS / 32;
-  __shared__ u32 s_w[WARPS];
+  __shared__ u32 s_w[WARPS], s_h[WARPS];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const u32 l0 = blockIdx.x * (u32)(THREADS * IPT) + (u32)tid * IPT;
-  u32 v = NO_TAIL_IDX;
+  u32 v = NO_TAIL_IDX, hd = 0;  // first run-tail index, last run-head index + 1
   if (l0 < a.S) {
     const u32 nvalid = min((u32)IPT, a.S - l0);
+    u32 prev = (l0 > 0) ? (u32)(a.keys[l0 - 1] >> a.lab_bits) : 0u;
     u32 lab = (u32)(a.keys[l0] >> a.lab_bits);
     for (u32 j = 0; j < nvalid; ++j) {
       const u32 l = l0 + j;
       const bool last = l + 1 >= a.S;
       const u32 nlab = last ? 0u : (u32)(a.keys[l + 1] >> a.lab_bits);
-      if (last || nlab != lab) { v = l; break; }
+      if (l == 0 || lab != prev) hd = l + 1u;
+      if ((last || nlab != lab) && v == NO_TAIL_IDX) v = l;
+      prev = lab;
       lab = nlab;
     }
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
-  if (lane == 0) s_w[warp] = v;
+  for (int o = 16; o > 0; o >>= 1) {
+    v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+    hd = max(hd, __shfl_xor_sync(0xffffffffu, hd, o));
+  }
+  if (lane == 0) { s_w[warp] = v; s_h[warp] = hd; }
   __syncthreads();
   if (tid == 0) {
-    u32 m = NO_TAIL_IDX;
+    u32 m = NO_TAIL_IDX, h = 0;
 #pragma unroll
-    for (int w = 0; w < WARPS; ++w) m = min(m, s_w[w]);
+    for (int w = 0; w < WARPS; ++w) { m = min(m, s_w[w]); h = max(h, s_h[w]); }
     a.tile_rtail[blockIdx.x] = m;
+    a.tile_rhead[blockIdx.x] = h;
   }
 }
 
@@ -660,7 +652,6 @@ __global__ void __launch_bounds__(THREADS, 2) k_slots(const SlotArgs a) {
   constexpr int WARPS = THREADS / 32;
   constexpr int TILE = THREADS * IPT;
   __shared__ u32 s_wh[WARPS], s_wt[WARPS];
-  __shared__ u32 s_pre;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const u32 tile = blockIdx.x;
   const u32 S = a.S;
@@ -707,41 +698,14 @@ __global__ void __launch_bounds__(THREADS, 2) k_slots(const SlotArgs a) {
   if (lane == 0) eh = 0;
   if (lane == 31) et = NO_TAIL_IDX;
   __syncthreads();
-  u32 bh = 0;
 #pragma unroll
   for (int w = 0; w < WARPS; ++w) {
     if (w < warp) eh = max(eh, s_wh[w]);
     if (w > warp) et = min(et, s_wt[w]);
-    bh = max(bh, s_wh[w]);
   }
+  // carries across tiles come from k_run_summary + k_tail_scan: no block waits for another one
   et = min(et, a.next_rtail[tile]);
-  // tile prefix: run head index + 1 of the last run start before this tile (decoupled look-back)
-  if (warp == 0) {
-    u32 xh = 0;
-    if (tile == 0) {
-      if (lane == 0) st_volatile_u64(a.status, ST_PRE | bh);
-    } else {
-      if (lane == 0) st_volatile_u64(a.status + tile, ST_AGG | bh);
-      i64 look = (i64)tile - 1 - lane;
-      for (;;) {
-        u64 sv = ST_PRE;
-        if (look >= 0) {
-          do { sv = ld_volatile_u64(a.status + look); } while ((sv & ST_FLAG) == 0);
-        }
-        const u32 pre = __ballot_sync(0xffffffffu, (sv & ST_FLAG) == ST_PRE);
-        const int first = pre ? (__ffs(pre) - 1) : 32;
-        u32 vh = (lane <= first) ? (u32)(sv & 0xffffffffull) : 0u;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) vh = max(vh, __shfl_xor_sync(0xffffffffu, vh, o));
-        xh = max(xh, vh);
-        if (pre) break;
-        look -= 32;
-      }
-      if (lane == 0) st_volatile_u64(a.status + tile, ST_PRE | max(xh, bh));
-    }
-    if (lane == 0) s_pre = xh;
-  }
-  __syncthreads();
+  eh = max(eh, a.prev_rhead[tile]);
   u32 rt[IPT];  // run tail index of every element
   {
     u32 cur = et;
@@ -751,7 +715,7 @@ __global__ void __launch_bounds__(THREADS, 2) k_slots(const SlotArgs a) {
       rt[j] = cur;
     }
   }
-  u32 rh = max(s_pre, eh);  // run head index + 1
+  u32 rh = eh;  // run head index + 1
   u32 gs = 0, ge = 0, rho = 0;
   bool has_rho = false;
 #pragma unroll
@@ -1333,7 +1297,7 @@ struct Layout {
   u32 *hlist[2]; u32 hcap;     // labels of the huge groups
   u32 *hcount;                 // [2]
   u32 *gupd; u32 *gupd_count;  // end-of-inert-block updates of one round
-  u64 *slot_status; u32 *tile_rtail, *next_rtail;
+  u32 *tile_rtail, *next_rtail;
   u32 *ghist;      // [MAX_PASSES][256]
   u32 *bin_base;   // [MAX_PASSES][256]
   u32 *present;    // [256]
@@ -1386,7 +1350,6 @@ Layout make_layout(char *base, u32 n) {
   y.next_tail = c.take<u32>(rtiles + 1);
   y.tile_head = c.take<u32>(rtiles + 1);
   y.prev_head = c.take<u32>(rtiles + 1);
-  y.slot_status = c.take<u64>(rtiles + 1);
   y.tile_rtail = c.take<u32>(rtiles + 1);
   y.next_rtail = c.take<u32>(rtiles + 1);
   for (int i = 0; i < 2; ++i) { y.bag_sufx[i] = c.take<u32>(N); y.bag_pos[i] = c.take<u32>(N); }
@@ -1824,13 +1787,12 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
       const u32 tiles = (u32)div_up(S, RB_TILE);
       SlotArgs sa;
       sa.keys = y.keys[cur]; sa.S = S; sa.lab_bits = lab_bits; sa.G = y.G; sa.rho = y.rho; sa.round = round;
-      sa.filter = filter ? 1 : 0; sa.slots = y.slots; sa.status = y.slot_status;
-      sa.tile_rtail = y.tile_rtail; sa.next_rtail = y.next_rtail; sa.gupd = y.gupd; sa.gupd_count = y.gupd_count;
-      GSA_TRY(cudaMemsetAsync(y.slot_status, 0, (size_t)tiles * sizeof(u64), st));
+      sa.filter = filter ? 1 : 0; sa.slots = y.slots;
+      sa.tile_rtail = y.tile_rtail; sa.next_rtail = y.next_rtail; sa.tile_rhead = y.tile_head; sa.prev_rhead = y.prev_head; sa.gupd = y.gupd; sa.gupd_count = y.gupd_count;
       GSA_TRY(cudaMemsetAsync(y.gupd_count, 0, sizeof(u32), st));
       k_run_summary<RB_THREADS, RB_IPT><<<tiles, RB_THREADS, 0, st>>>(sa);
       KLAUNCH_CHECK();
-      k_tail_scan<<<1, 1024, 0, st>>>(y.tile_rtail, y.next_rtail, tiles, nullptr, nullptr);
+      k_tail_scan<<<1, 1024, 0, st>>>(y.tile_rtail, y.next_rtail, tiles, y.tile_head, y.prev_head);
       KLAUNCH_CHECK();
       k_slots<RB_THREADS, RB_IPT><<<tiles, RB_THREADS, 0, st>>>(sa);
       KLAUNCH_CHECK();

@@ -3,7 +3,7 @@
 ncu's CSV source page is SASS-only; this joins it with `nvdisasm -g` of the in-tree libgsa.so
 (same build as the one profiled) and sums executed instructions and stall samples per .cu line.
 
-Usage: python tools/ncu_lines.py <capture.ncu-rep> <kernel-name-substring> [top]
+Usage: python tools/ncu_lines.py <capture.ncu-rep> <kernel-name-substring> [top] [launch index in the capture]
 """
 import collections
 import csv
@@ -49,9 +49,14 @@ def main():
     table, fname = line_table(sub)
     out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
-    hdr = rows[1]
+    # the page holds one block per captured launch: "Kernel Name" row, header row, SASS rows
+    starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]
+    which = int(sys.argv[4]) if len(sys.argv) > 4 else 0
+    lo = starts[which]
+    hi = starts[which + 1] if which + 1 < len(starts) else len(rows)
+    hdr = rows[lo + 1]
     ci = {h: i for i, h in enumerate(hdr)}
-    body = [r for r in rows[2:] if len(r) == len(hdr)]
+    body = [r for r in rows[lo + 2:hi] if len(r) == len(hdr)]
     base = int(body[0][0], 16)
     agg = collections.defaultdict(lambda: [0.0, 0.0, collections.Counter()])
     stalls = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
