@@ -234,7 +234,7 @@ __device__ __forceinline__ bool is_huge_label(u32 lab) { return (lab & (HUGE_M -
 //   other even label   : medium, sorted through the text-order path every round
 //   odd label          : tiny, lives in the bag; always the canonical label of its slot range
 // (tiny_max == 0 switches the tiny class off: sparse mode, which keeps no label for most suffixes.)
-constexpr u32 TINY_MAX = 128;
+constexpr u32 TINY_MAX = 32;
 constexpr u32 BAG_HEAD = 0x80000000u;  // bag entry: first member of its group
 
 __device__ __forceinline__ u32 tiny_label(u32 s) { return (s & 1u) ? s + 2u : s + 1u; }  // first odd label in [s+1, ..]
@@ -1176,13 +1176,11 @@ struct BagArgs {
 
 __global__ void __launch_bounds__(BAG_THREADS) k_bag_refine(const BagArgs a) {
   constexpr u32 NW = BAG_THREADS / 32;
-  static_assert(NW <= 32, "warp totals are scanned by one warp");
   __shared__ u32 s_sfx[BAG_THREADS], s_r2[BAG_THREADS];
   __shared__ u32 s_slot[BAG_THREADS];  // new slot, bit 31 = survives (its run has more than one member)
-  __shared__ u32 s_excl[BAG_THREADS];  // survivors before this entry (block order)
   __shared__ u32 s_gs[BAG_THREADS];    // slot of the entry (first slot of the group at a head)
   __shared__ u32 s_headm[NW];          // per warp: which entries start a group
-  __shared__ u32 s_warp[32];
+  __shared__ u32 s_warp[NW], s_bal[NW];  // survivors per warp: count, lane mask
   __shared__ u32 s_base;
   const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
   const u32 l = blockIdx.x * (u32)BAG_TILE + tid;
@@ -1226,21 +1224,14 @@ __global__ void __launch_bounds__(BAG_THREADS) k_bag_refine(const BagArgs a) {
   // output position: survivors of earlier groups of the block (block order), then the survivors of
   // my own group in slot order -- the new groups stay contiguous, each headed by its first slot
   const u32 bal = __ballot_sync(0xffffffffu, surv);
-  if ((tid & 31u) == 0u) s_warp[tid >> 5] = (u32)__popc(bal);
+  if (lane == 0u) { s_warp[warp] = (u32)__popc(bal); s_bal[warp] = bal; }
   __syncthreads();
-  if (tid < 32u) {  // exclusive scan of the warp totals
-    const u32 v = (tid < NW) ? s_warp[tid] : 0u;
-    u32 inc = v;
+  if (tid == 0u) {
+    u32 tot = 0;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const u32 t = __shfl_up_sync(0xffffffffu, inc, o);
-      if ((int)tid >= o) inc += t;
-    }
-    s_warp[tid] = inc - v;
-    if (tid == 31u) s_base = inc ? atomicAdd(a.count_out, inc) : 0u;
+    for (u32 w = 0; w < NW; ++w) tot += s_warp[w];
+    s_base = tot ? atomicAdd(a.count_out, tot) : 0u;
   }
-  __syncthreads();
-  s_excl[tid] = s_warp[tid >> 5] + (u32)__popc(bal & ((1u << (tid & 31u)) - 1u));
   __syncthreads();
   if (!mine) return;
   const u32 sufx = s_sfx[tid];
@@ -1255,7 +1246,9 @@ __global__ void __launch_bounds__(BAG_THREADS) k_bag_refine(const BagArgs a) {
     in_group_before += ((sm & BAG_HEAD) && (sm & ~BAG_HEAD) < slot) ? 1u : 0u;
   }
   if (tiny_label(s1) != tiny_label(gs)) a.rank[sufx] = tiny_label(s1);
-  const u32 o = s_base + s_excl[g0] + in_group_before;
+  u32 before_group = (u32)__popc(s_bal[g0 >> 5] & ((1u << (g0 & 31u)) - 1u));  // survivors in front of my group's head
+  for (u32 w = 0; w < (g0 >> 5); ++w) before_group += s_warp[w];
+  const u32 o = s_base + before_group + in_group_before;
   a.sufx_out[o] = sufx;
   a.pos_out[o] = slot | (slot == s1 ? BAG_HEAD : 0u);
 }
