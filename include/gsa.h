@@ -109,6 +109,19 @@ int32_t gsa_divbwt(const uint8_t *T, uint8_t *U, int32_t *A, int32_t n);
 int32_t gsa_bwt_device(const uint8_t *d_T, const int32_t *d_SA, int32_t n, uint8_t *d_U, int32_t *primary_index,
                        void *stream);
 
+/* Longest-common-prefix array: LCP[0] = 0, LCP[j] = lcp(suffix SA[j-1], suffix SA[j]).
+ * The reference has no LCP routine; this is the extension SURVEY.md section 8(f) ranks third
+ * (its sa_search, c-sources/utils.c:275-286, carries lmatch/rmatch instead).  Oracle: Kasai's
+ * algorithm (oracle/oracle.c).  gsa_lcp_device takes device pointers of a resident text and
+ * suffix array (workspace: gsa_lcp_workspace_bytes(n) bytes, or NULL to allocate internally);
+ * gsa_lcp takes HOST pointers; gsa_divsufsort_lcp builds SA and LCP in one call (either output
+ * may be NULL).  Returns 0, or a negative error code. */
+size_t gsa_lcp_workspace_bytes(int32_t n);
+int32_t gsa_lcp_device(const uint8_t *d_T, const int32_t *d_SA, int32_t *d_LCP, int32_t n, void *workspace,
+                       size_t workspace_bytes, void *stream);
+int32_t gsa_lcp(const uint8_t *T, const int32_t *SA, int32_t *LCP, int32_t n, int32_t device);
+int32_t gsa_divsufsort_lcp(const uint8_t *T, int32_t *SA, int32_t *LCP, int32_t n, int32_t device);
+
 /* O(n) validity check of a suffix array on the GPU (device pointers).
  * Replaces sacabase::verify (crates/sacabase/src/lib.rs:127-149) / sufcheck
  * (c-sources/utils.c:160-241) at sizes where the O(n * LCP) pairwise check is

@@ -197,6 +197,25 @@ int32_t oracle_sa_search(const uint8_t *T, int32_t Tsize, const uint8_t *P, int3
 /* ------------------------------------------------------------------------- */
 /* libdivsufsort sufcheck, non-verbose  (utils.c:160-241)                     */
 /* ------------------------------------------------------------------------- */
+int32_t oracle_lcp_kasai(const uint8_t *T, const int32_t *SA, int32_t n, int32_t *LCP) {
+  if (n < 0 || (n > 0 && (!T || !SA || !LCP))) return -1;
+  if (n == 0) return 0;
+  int32_t *isa = (int32_t *)malloc((size_t)n * sizeof(int32_t));
+  if (!isa) return -1;
+  for (int32_t j = 0; j < n; ++j) isa[SA[j]] = j;
+  int32_t l = 0;
+  for (int32_t i = 0; i < n; ++i) {
+    const int32_t j = isa[i];
+    if (j == 0) { LCP[0] = 0; l = 0; continue; }
+    const int32_t p = SA[j - 1];
+    while (i + l < n && p + l < n && T[i + l] == T[p + l]) ++l;
+    LCP[j] = l;
+    if (l > 0) --l;
+  }
+  free(isa);
+  return 0;
+}
+
 int32_t oracle_sufcheck(const uint8_t *T, const int32_t *SA, int32_t n) {
   if (!T || !SA || n < 0) return -1;
   if (n == 0) return 0;

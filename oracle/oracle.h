@@ -61,6 +61,11 @@ int32_t oracle_sa_search(const uint8_t *T, int32_t Tsize, const uint8_t *P, int3
 /* libdivsufsort sufcheck (non-verbose): 0 ok, -1..-4 as utils.c:160-241. */
 int32_t oracle_sufcheck(const uint8_t *T, const int32_t *SA, int32_t n);
 
+/* LCP array by Kasai et al. (CPM 2001): LCP[0] = 0, LCP[j] = lcp(suffix SA[j-1], suffix SA[j]).
+ * No counterpart in the reference (SURVEY.md 8(f) rank 3 extension); pinned in tests/ against a
+ * byte-by-byte comparison of adjacent suffixes.  Returns 0, -1 on bad arguments / allocation. */
+int32_t oracle_lcp_kasai(const uint8_t *T, const int32_t *SA, int32_t n, int32_t *LCP);
+
 /* sacapart chunking (lib.rs:43-51,60-62): partition_size = n / P + 1, number of
  * chunks actually produced by par_chunks.  Returns -1 if P == 0 (division by zero
  * in the reference). */

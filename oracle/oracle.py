@@ -71,6 +71,8 @@ class _Port:
         L.oracle_sa_search.restype = C.c_int32
         L.oracle_sufcheck.argtypes = [_u8p, _i32p, C.c_int32]
         L.oracle_sufcheck.restype = C.c_int32
+        L.oracle_lcp_kasai.argtypes = [_u8p, _i32p, C.c_int32, _i32p]
+        L.oracle_lcp_kasai.restype = C.c_int32
         L.oracle_part_plan.argtypes = [C.c_uint64, C.c_uint64, _u64p, _u64p]
         L.oracle_part_plan.restype = C.c_int32
         L.oracle_part_lsm.argtypes = [_u8p, C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(_i32p), _u8p, C.c_size_t, _u64p, _u64p]
@@ -100,6 +102,17 @@ class _Port:
         if t.size == 0:
             return 0
         return self.lib.oracle_sufcheck(_ptr(t, _u8p), _ptr(sa, _i32p), t.size)
+
+    def lcp(self, text, sa) -> np.ndarray:
+        """LCP[0] = 0, LCP[j] = lcp(suffix sa[j-1], suffix sa[j]) (Kasai)."""
+        t = _as_u8(text)
+        sa = np.ascontiguousarray(sa, dtype=np.int32)
+        out = np.zeros(t.size, np.int32)
+        if t.size:
+            rc = self.lib.oracle_lcp_kasai(_ptr(t, _u8p), _ptr(sa, _i32p), t.size, _ptr(out, _i32p))
+            if rc != 0:
+                raise RuntimeError(f"oracle_lcp_kasai rc={rc}")
+        return out
 
     def verify(self, text, sa):
         t = _as_u8(text)

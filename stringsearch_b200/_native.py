@@ -98,6 +98,10 @@ def _load() -> C.CDLL:
         "gsa_build_device": ([vp, vp, C.c_int32, vp, C.c_size_t, vp, C.POINTER(BuildStats)], C.c_int32),
         "gsa_divbwt": ([vp, vp, vp, C.c_int32], C.c_int32),
         "gsa_bwt_device": ([vp, vp, C.c_int32, vp, i32p, vp], C.c_int32),
+        "gsa_lcp_workspace_bytes": ([C.c_int32], C.c_size_t),
+        "gsa_lcp_device": ([vp, vp, vp, C.c_int32, vp, C.c_size_t, vp], C.c_int32),
+        "gsa_lcp": ([vp, vp, vp, C.c_int32, C.c_int32], C.c_int32),
+        "gsa_divsufsort_lcp": ([vp, vp, vp, C.c_int32, C.c_int32], C.c_int32),
         "gsa_sufcheck_device": ([vp, vp, C.c_int32, vp, i64p], C.c_int32),
         "gsa_sufcheck": ([vp, vp, C.c_int32, C.c_int32, i64p], C.c_int32),
         "gsa_index_create": ([vp, C.c_int64, C.c_int32, C.POINTER(vp), C.POINTER(BuildStats)], C.c_int32),

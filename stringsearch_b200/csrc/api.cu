@@ -280,6 +280,54 @@ int32_t gsa_bwt_device(const uint8_t *d_T, const int32_t *d_SA, int32_t n, uint8
   return bwt_device(d_T, d_SA, (u32)n, d_U, primary_index, static_cast<cudaStream_t>(stream));
 }
 
+size_t gsa_lcp_workspace_bytes(int32_t n) { return lcp_workspace_bytes(n < 0 ? 0u : (u32)n); }
+
+int32_t gsa_lcp_device(const uint8_t *d_T, const int32_t *d_SA, int32_t *d_LCP, int32_t n, void *workspace,
+                       size_t workspace_bytes, void *stream) {
+  if (n < 0 || (n > 0 && (!d_T || !d_SA || !d_LCP))) return GSA_EINVAL;
+  return lcp_device(d_T, d_SA, (u32)n, d_LCP, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+// Host-pointer forms.  build != 0: the suffix array is built here (SA may then be NULL = not wanted).
+static int32_t lcp_host(const uint8_t *T, int32_t *SA, int32_t *LCP, int32_t n, int32_t device, int build) {
+  if (n < 0 || (n > 0 && (T == nullptr || (SA == nullptr && !build)))) return GSA_EINVAL;
+  if (n == 0) return GSA_OK;
+  DeviceGuard dg(device);
+  if (!dg.ok) return GSA_ECUDA;
+  Stream st;
+  GSA_TRY_RC(st.create());
+  const size_t text_bytes = align_up((size_t)n + 64, 256), sa_bytes = align_up((size_t)n * sizeof(i32), 256);
+  const size_t ws_bytes = std::max(build ? build_workspace_bytes((u32)n) : (size_t)0, sa_bytes + lcp_workspace_bytes((u32)n));
+  Scratch sc;
+  GSA_TRY_RC(sc.acquire(device, text_bytes + sa_bytes + ws_bytes));
+  u8 *d_T = reinterpret_cast<u8 *>(sc.p);
+  i32 *d_SA = reinterpret_cast<i32 *>(sc.p + text_bytes);
+  char *d_ws = sc.p + text_bytes + sa_bytes;
+  GSA_TRY(cudaMemcpyAsync(d_T, T, (size_t)n, cudaMemcpyHostToDevice, st.s));
+  if (build) {
+    GSA_TRY_RC(build_sa_device(d_T, d_SA, (u32)n, d_ws, ws_bytes, st.s, nullptr));
+    if (SA) GSA_TRY(cudaMemcpyAsync(SA, d_SA, (size_t)n * sizeof(i32), cudaMemcpyDeviceToHost, st.s));
+  } else {
+    GSA_TRY(cudaMemcpyAsync(d_SA, SA, (size_t)n * sizeof(i32), cudaMemcpyHostToDevice, st.s));
+  }
+  if (LCP) {
+    i32 *d_LCP = reinterpret_cast<i32 *>(d_ws);  // the sort workspace is free again
+    GSA_TRY_RC(lcp_device(d_T, d_SA, (u32)n, d_LCP, d_ws + sa_bytes, ws_bytes - sa_bytes, st.s));
+    GSA_TRY(cudaMemcpyAsync(LCP, d_LCP, (size_t)n * sizeof(i32), cudaMemcpyDeviceToHost, st.s));
+  }
+  GSA_TRY(cudaStreamSynchronize(st.s));
+  return GSA_OK;
+}
+
+int32_t gsa_lcp(const uint8_t *T, const int32_t *SA, int32_t *LCP, int32_t n, int32_t device) {
+  if (n > 0 && LCP == nullptr) return GSA_EINVAL;
+  return lcp_host(T, const_cast<int32_t *>(SA), LCP, n, device, 0);
+}
+
+int32_t gsa_divsufsort_lcp(const uint8_t *T, int32_t *SA, int32_t *LCP, int32_t n, int32_t device) {
+  return lcp_host(T, SA, LCP, n, device, 1);
+}
+
 int32_t gsa_sufcheck_device(const uint8_t *d_T, const int32_t *d_SA, int32_t n, void *stream, int64_t *bad_index) {
   if (n < 0 || (n > 0 && (d_T == nullptr || d_SA == nullptr))) return GSA_EINVAL;
   return sufcheck_device(d_T, d_SA, (u32)n, static_cast<cudaStream_t>(stream), bad_index);

@@ -20,6 +20,11 @@ int sufcheck_device(const u8 *d_T, const i32 *d_SA, u32 n, cudaStream_t st, i64 
 // bwt.cu
 int bwt_device(const u8 *d_T, const i32 *d_SA, u32 n, u8 *d_U, i32 *primary_index, cudaStream_t st);
 
+// lcp.cu
+size_t lcp_workspace_bytes(u32 n);
+int lcp_device(const u8 *d_T, const i32 *d_SA, u32 n, i32 *d_LCP, void *workspace, size_t workspace_bytes,
+               cudaStream_t st);
+
 // search.cu
 // Text view of an index: the suffix array covers text[0, n); text_avail >= n bytes are
 // readable (halo behind a shard, used only by the may_extend rule).

@@ -35,6 +35,17 @@ void set_error(const char *what, const char *file, int line);
 
 static inline u64 div_up(u64 a, u64 b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
+// Carves 256-byte aligned arrays out of one workspace block (p may be null: size computation only).
+struct Carve {
+  char *p;
+  size_t used;
+  template <typename T>
+  T *take(size_t count) {
+    T *r = reinterpret_cast<T *>(p + used);
+    used += align_up(count * sizeof(T), 256);
+    return r;
+  }
+};
 // bits needed to represent values 0..v  (bits_for(0) = 1 so a key is never 0 bits wide)
 static inline u32 bits_for(u64 v) {
   u32 b = 1;

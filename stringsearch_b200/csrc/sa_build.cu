@@ -1269,17 +1269,6 @@ constexpr int GA_THREADS = 512;
 constexpr int GA_IPT = 8;
 constexpr int GA_BLOCKS_PER_SM = 2;
 
-struct Carve {
-  char *p;
-  size_t used;
-  template <typename T>
-  T *take(size_t count) {
-    T *r = reinterpret_cast<T *>(p + used);
-    used += align_up(count * sizeof(T), 256);
-    return r;
-  }
-};
-
 struct Layout {
   u64 *packed; u64 packed_words;
   u64 *keys[2]; u32 *vals[2]; u32 *slots; u32 *lst[2]; u32 *rank;

@@ -54,3 +54,31 @@ def bwt(text):
                           N.ptr(u) if u.size else N.ptr(np.zeros(1, np.uint8)), None, t.size)
     assert rc >= 0, f"divbwt returned {rc}: {N.last_error()}"
     return u, rc
+
+
+def lcp(text, sa, device: int | None = None) -> np.ndarray:
+    """LCP array of a suffix array: LCP[0] = 0, LCP[j] = lcp(suffix sa[j-1], suffix sa[j]).
+    (No counterpart in the reference)"""
+    t = N.as_u8(text)
+    s = np.ascontiguousarray(sa, dtype=np.int32)
+    assert s.size == t.size, "sa and text must have the same length"
+    out = np.zeros(t.size, dtype=np.int32)
+    if t.size:
+        rc = N.lib.gsa_lcp(N.ptr(t), N.ptr(s), N.ptr(out), t.size, 0 if device is None else device)
+        if rc != 0:
+            raise N.GsaError(rc, "gsa_lcp", N.last_error())
+    return out
+
+
+def sort_with_lcp(text, device: int | None = None):
+    """-> (SuffixArray, LCP) from one call: the text is uploaded once and the suffix array never
+    leaves the device between the two steps."""
+    t = N.as_u8(text)
+    assert t.size < I32_MAX, f"text too large, should not exceed {I32_MAX - 1} bytes"
+    sa = np.zeros(t.size, dtype=np.int32)
+    out = np.zeros(t.size, dtype=np.int32)
+    if t.size:
+        rc = N.lib.gsa_divsufsort_lcp(N.ptr(t), N.ptr(sa), N.ptr(out), t.size, 0 if device is None else device)
+        if rc != 0:
+            raise N.GsaError(rc, "gsa_divsufsort_lcp", N.last_error())
+    return SuffixArray(t, sa), out

@@ -58,6 +58,29 @@ def test_sufcheck_and_verify(port, ref):
         assert port.sufcheck(c, s) == 0 and port.verify(c, s)[0] == 0
 
 
+def _lcp_bruteforce(t: bytes, sa) -> list:
+    out = [0] * len(sa)
+    for j in range(1, len(sa)):
+        a, b = t[sa[j - 1]:], t[sa[j]:]
+        l = 0
+        while l < len(a) and l < len(b) and a[l] == b[l]:
+            l += 1
+        out[j] = l
+    return out
+
+
+def test_lcp_oracle_matches_definition(port, sa_golden):
+    """oracle_lcp_kasai (the checker of the GPU LCP kernels) against the definition itself:
+    LCP[0] = 0, LCP[j] = common prefix length of the suffixes at SA[j-1] and SA[j]."""
+    cases = [bytes(t) for _, t, _ in sa_golden if len(t) <= 3000]
+    cases += [b"", b"a", b"aa", b"ab", b"banana", b"mississippi", b"a" * 200, b"ab" * 150, b"abcabcabcabd" * 20]
+    cases += [bytes(c) for c in random_cases(seed=17, sizes=(10, 100, 700))]
+    for t in cases:
+        sa = port.sa_build(t)
+        assert port.lcp(t, sa).tolist() == _lcp_bruteforce(t, sa.tolist()), t[:20]
+    assert port.lcp(b"banana", port.sa_build(b"banana")).tolist() == [0, 1, 3, 0, 0, 2]
+
+
 def test_lsm_golden(port, ref, search_golden):
     w = search_golden["worse_test"]
     t = w["text"].encode()
