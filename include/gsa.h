@@ -104,10 +104,19 @@ int32_t gsa_build_device(const uint8_t *d_T, int32_t *d_SA, int32_t n, void *wor
  * pointers.  gsa_bwt_device is the device-pointer form of bw_transform (utils.c:52-110) for a
  * suffix array that is already resident: U[0] = T[n-1], then T[SA[i]-1] for SA[i] != 0 in SA
  * order; *primary_index = slot of suffix 0, plus one.
- * (inverse_bw_transform is a sequential LF-mapping walk and is not part of the GPU path.) */
+ * gsa_inverse_bw_transform replaces inverse_bw_transform(T, U, A, n, idx) (utils.c:111-156): same
+ * signature, argument checks and return codes (0; -1 for T/U NULL, n < 0, idx < 0, n < idx or
+ * n > 0 with idx == 0; -2 out of memory); `A` is ignored.  HOST pointers.  The reference's
+ * sequential psi walk is done as a list ranking on the GPU.  (n == 1: U[0] = T[0]; the reference
+ * returns without writing U.)  gsa_inverse_bwt_device is the device-pointer form (workspace:
+ * gsa_inverse_bwt_workspace_bytes(n) bytes, or NULL to allocate internally). */
 int32_t gsa_divbwt(const uint8_t *T, uint8_t *U, int32_t *A, int32_t n);
 int32_t gsa_bwt_device(const uint8_t *d_T, const int32_t *d_SA, int32_t n, uint8_t *d_U, int32_t *primary_index,
                        void *stream);
+int32_t gsa_inverse_bw_transform(const uint8_t *T, uint8_t *U, int32_t *A, int32_t n, int32_t idx);
+size_t gsa_inverse_bwt_workspace_bytes(int32_t n);
+int32_t gsa_inverse_bwt_device(const uint8_t *d_T, uint8_t *d_U, int32_t n, int32_t idx, void *workspace,
+                               size_t workspace_bytes, void *stream);
 
 /* Longest-common-prefix array: LCP[0] = 0, LCP[j] = lcp(suffix SA[j-1], suffix SA[j]).
  * The reference has no LCP routine; this is the extension SURVEY.md section 8(f) ranks third

@@ -239,6 +239,17 @@ class _Ref:
         up = _ptr(u, _u8p) if u.size else _ptr(np.zeros(1, np.uint8), _u8p)
         return u, self.lib.divbwt(tp, up, None, t.size)
 
+    def inverse_bwt(self, u, idx: int):
+        """reference inverse_bw_transform -> (rc, text)"""
+        b = _as_u8(u)
+        out = np.zeros(b.size, dtype=np.uint8)
+        one = np.zeros(1, np.uint8)
+        self.lib.inverse_bw_transform.argtypes = [_u8p, _u8p, _i32p, C.c_int32, C.c_int32]
+        self.lib.inverse_bw_transform.restype = C.c_int32
+        rc = self.lib.inverse_bw_transform(_ptr(b, _u8p) if b.size else _ptr(one, _u8p),
+                                           _ptr(out, _u8p) if out.size else _ptr(one, _u8p), None, b.size, int(idx))
+        return rc, out
+
     def divsufsort_raw(self, tptr, saptr, n) -> int:
         return self.lib.divsufsort(tptr, saptr, n)
 

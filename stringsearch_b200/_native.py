@@ -98,6 +98,9 @@ def _load() -> C.CDLL:
         "gsa_build_device": ([vp, vp, C.c_int32, vp, C.c_size_t, vp, C.POINTER(BuildStats)], C.c_int32),
         "gsa_divbwt": ([vp, vp, vp, C.c_int32], C.c_int32),
         "gsa_bwt_device": ([vp, vp, C.c_int32, vp, i32p, vp], C.c_int32),
+        "gsa_inverse_bw_transform": ([vp, vp, vp, C.c_int32, C.c_int32], C.c_int32),
+        "gsa_inverse_bwt_workspace_bytes": ([C.c_int32], C.c_size_t),
+        "gsa_inverse_bwt_device": ([vp, vp, C.c_int32, C.c_int32, vp, C.c_size_t, vp], C.c_int32),
         "gsa_lcp_workspace_bytes": ([C.c_int32], C.c_size_t),
         "gsa_lcp_device": ([vp, vp, vp, C.c_int32, vp, C.c_size_t, vp], C.c_int32),
         "gsa_lcp": ([vp, vp, vp, C.c_int32, C.c_int32], C.c_int32),

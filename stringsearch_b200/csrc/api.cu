@@ -280,6 +280,37 @@ int32_t gsa_bwt_device(const uint8_t *d_T, const int32_t *d_SA, int32_t n, uint8
   return bwt_device(d_T, d_SA, (u32)n, d_U, primary_index, static_cast<cudaStream_t>(stream));
 }
 
+// inverse_bw_transform(T, U, A, n, idx) (c-sources/utils.c:111-156).  Host pointers; `A` is ignored.
+int32_t gsa_inverse_bw_transform(const uint8_t *T, uint8_t *U, int32_t *A, int32_t n, int32_t idx) {
+  (void)A;
+  if (T == nullptr || U == nullptr || n < 0 || idx < 0 || n < idx || (0 < n && idx == 0)) return GSA_EINVAL;  // utils.c:120-123
+  if (n <= 1) { if (n == 1) U[0] = T[0]; return GSA_OK; }
+  const int device = current_device();
+  DeviceGuard dg(device);
+  if (!dg.ok) return GSA_ECUDA;
+  Stream st;
+  GSA_TRY_RC(st.create());
+  const size_t text_bytes = align_up((size_t)n + 64, 256);
+  const size_t ws_bytes = inverse_bwt_workspace_bytes((u32)n);
+  Scratch sc;
+  GSA_TRY_RC(sc.acquire(device, 2 * text_bytes + ws_bytes));
+  u8 *d_T = reinterpret_cast<u8 *>(sc.p);
+  u8 *d_U = reinterpret_cast<u8 *>(sc.p + text_bytes);
+  GSA_TRY(cudaMemcpyAsync(d_T, T, (size_t)n, cudaMemcpyHostToDevice, st.s));
+  GSA_TRY_RC(inverse_bwt_device(d_T, d_U, (u32)n, (u32)idx, sc.p + 2 * text_bytes, ws_bytes, st.s));
+  GSA_TRY(cudaMemcpyAsync(U, d_U, (size_t)n, cudaMemcpyDeviceToHost, st.s));
+  GSA_TRY(cudaStreamSynchronize(st.s));
+  return GSA_OK;
+}
+
+size_t gsa_inverse_bwt_workspace_bytes(int32_t n) { return inverse_bwt_workspace_bytes(n < 0 ? 0u : (u32)n); }
+
+int32_t gsa_inverse_bwt_device(const uint8_t *d_T, uint8_t *d_U, int32_t n, int32_t idx, void *workspace,
+                               size_t workspace_bytes, void *stream) {
+  if (n < 0 || idx < 0 || n < idx || (0 < n && (idx == 0 || !d_T || !d_U))) return GSA_EINVAL;
+  return inverse_bwt_device(d_T, d_U, (u32)n, (u32)idx, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
 size_t gsa_lcp_workspace_bytes(int32_t n) { return lcp_workspace_bytes(n < 0 ? 0u : (u32)n); }
 
 int32_t gsa_lcp_device(const uint8_t *d_T, const int32_t *d_SA, int32_t *d_LCP, int32_t n, void *workspace,

@@ -13,12 +13,20 @@ size_t build_workspace_bytes(u32 n);
 int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t workspace_bytes, cudaStream_t st,
                     gsa_build_stats *stats);
 
+// Stable order of a byte string (one radix pass): order[q] = index of the q-th byte in (value, index)
+// order; counts[256] (device, optional) receives the byte histogram.
+size_t byte_order_workspace_bytes(u32 n);
+int stable_byte_order_device(const u8 *d_bytes, u32 n, u32 *d_order, u32 *d_counts, void *workspace, size_t workspace_bytes,
+                             cudaStream_t st);
+
 // verify.cu
 size_t sufcheck_workspace_bytes(u32 n);
 int sufcheck_device(const u8 *d_T, const i32 *d_SA, u32 n, cudaStream_t st, i64 *bad_index);
 
 // bwt.cu
 int bwt_device(const u8 *d_T, const i32 *d_SA, u32 n, u8 *d_U, i32 *primary_index, cudaStream_t st);
+size_t inverse_bwt_workspace_bytes(u32 n);
+int inverse_bwt_device(const u8 *d_T, u8 *d_U, u32 n, u32 idx, void *workspace, size_t workspace_bytes, cudaStream_t st);
 
 // lcp.cu
 size_t lcp_workspace_bytes(u32 n);

@@ -1806,4 +1806,69 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
   return GSA_OK;
 }
 
+// ------------------------------------------------------------------------------------
+// Stable order of a byte string: order[q] = index of the q-th byte in (value, index) order.
+// One onesweep pass of the radix kernel above, its keys generated from the packed bytes; used by
+// the inverse BWT (bwt.cu), where this order is the LF/psi permutation of the transform.
+// ------------------------------------------------------------------------------------
+namespace {
+struct ByteOrderLayout { u64 *packed; u64 nwords; u64 *keys_out; u32 *ghist, *bin_base, *skip_mask, *pass_status; size_t total; };
+ByteOrderLayout byte_order_layout(char *base, u32 n) {
+  ByteOrderLayout y;
+  Carve c{base, 0};
+  y.nwords = (u64)n / 8 + 4;
+  y.packed = c.take<u64>(y.nwords);
+  y.keys_out = c.take<u64>(n);
+  y.ghist = c.take<u32>(MAX_PASSES * RADIX);
+  y.bin_base = c.take<u32>(MAX_PASSES * RADIX);
+  y.skip_mask = c.take<u32>(64);
+  y.pass_status = c.take<u32>(256 + div_up(n, PASS_TILE) * RADIX);
+  y.total = c.used;
+  return y;
+}
+}  // namespace
+
+size_t byte_order_workspace_bytes(u32 n) { return byte_order_layout(nullptr, n == 0 ? 1 : n).total + 256; }
+
+int stable_byte_order_device(const u8 *d_bytes, u32 n, u32 *d_order, u32 *d_counts, void *workspace, size_t workspace_bytes,
+                             cudaStream_t st) {
+  if (n == 0) return GSA_OK;
+  if (workspace == nullptr || workspace_bytes < byte_order_workspace_bytes(n)) {
+    set_error("workspace too small", __FILE__, __LINE__);
+    return GSA_EINVAL;
+  }
+  const size_t mis = (256 - (reinterpret_cast<uintptr_t>(workspace) & 255)) & 255;
+  const ByteOrderLayout y = byte_order_layout(static_cast<char *>(workspace) + mis, n);
+  const int smem = (int)PassCfg<PASS_THREADS, PASS_IPT>::SMEM;
+  GSA_TRY(cudaFuncSetAttribute(k_radix_pass<PASS_THREADS, PASS_IPT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  int sms = kDefaultSMs, dev = 0;
+  GSA_TRY(cudaGetDevice(&dev));
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  CodeMap cm;
+  for (int c = 0; c < 256; ++c) cm.code[c] = (u8)c;
+  k_pack<<<(u32)div_up(y.nwords, 256), 256, 0, st>>>(d_bytes, n, 8, cm, y.packed, y.nwords);
+  KLAUNCH_CHECK();
+  const KeyGen gen{y.packed, n, 0, 8, 8};
+  GSA_TRY(cudaMemsetAsync(y.ghist, 0, MAX_PASSES * RADIX * sizeof(u32), st));
+  GSA_TRY(cudaMemsetAsync(y.skip_mask, 0, sizeof(u32), st));
+  const u32 hist_blocks = (u32)std::min<u64>((u64)sms * 4, std::max<u64>(1, div_up(n, HIST_THREADS)));
+  k_hist0<HIST_THREADS><<<hist_blocks, HIST_THREADS, 0, st>>>(gen, 1, y.ghist);
+  KLAUNCH_CHECK();
+  k_scan_hist<<<1, RADIX, 0, st>>>(y.ghist, y.bin_base, n, y.skip_mask);
+  KLAUNCH_CHECK();
+  const u32 tiles = (u32)div_up(n, PASS_TILE);
+  GSA_TRY(cudaMemsetAsync(y.pass_status, 0, (256 + (size_t)tiles * RADIX) * sizeof(u32), st));
+  PassArgs a;
+  a.keys_in = nullptr; a.vals_in = nullptr;
+  a.keys_out = y.keys_out; a.vals_out = d_order;
+  a.n = n; a.shift = 0;
+  a.bin_base = y.bin_base;
+  a.counter = y.pass_status; a.status = y.pass_status + 256;
+  a.gen = gen;
+  k_radix_pass<PASS_THREADS, PASS_IPT, true><<<tiles, PASS_THREADS, smem, st>>>(a);
+  KLAUNCH_CHECK();
+  if (d_counts) GSA_TRY(cudaMemcpyAsync(d_counts, y.ghist, RADIX * sizeof(u32), cudaMemcpyDeviceToDevice, st));
+  return GSA_OK;
+}
+
 }  // namespace gsa

@@ -56,6 +56,18 @@ def bwt(text):
     return u, rc
 
 
+def inverse_bwt(u, primary_index: int) -> np.ndarray:
+    """inverse_bw_transform (crates/cdivsufsort/c-sources/utils.c:111-156): (U, primary index) -> text."""
+    b = N.as_u8(u)
+    out = np.empty(b.size, dtype=np.uint8)
+    one = np.zeros(1, np.uint8)
+    rc = N.lib.gsa_inverse_bw_transform(N.ptr(b) if b.size else N.ptr(one), N.ptr(out) if out.size else N.ptr(one), None,
+                                        b.size, int(primary_index))
+    if rc != 0:
+        raise N.GsaError(rc, "gsa_inverse_bw_transform", N.last_error())
+    return out
+
+
 def lcp(text, sa, device: int | None = None) -> np.ndarray:
     """LCP array of a suffix array: LCP[0] = 0, LCP[j] = lcp(suffix sa[j-1], suffix sa[j]).
     (No counterpart in the reference)"""

@@ -190,6 +190,39 @@ def test_bwt_matches_reference(ref, sa_golden):
         assert pidx == epidx and (u == eu).all(), (len(t), pidx, epidx)
 
 
+def test_inverse_bwt_round_trip_and_reference(ref, sa_golden):
+    """gsa_inverse_bw_transform vs the reference's inverse_bw_transform (utils.c:111-156), and the
+    round trip text -> divbwt -> inverse == text, on inputs that cross the 1024-row splitter
+    stride, the 4096-element radix tile, and with one-symbol / two-symbol alphabets."""
+    from stringsearch_b200 import divsufsort, synth
+    from stringsearch_b200 import _native as N
+
+    rng = np.random.default_rng(12)
+    texts = [t for _, t, _ in sa_golden if len(t) > 0]
+    texts += [b"ab", b"ba", b"aa", b"banana", b"mississippi", np.zeros(5000, np.uint8), synth.acgt(300_000, 2),
+              synth.repetitive(500_000, 3, period=60), synth.random_bytes(100_001, 4), synth.random_bytes(1 << 20, 6),
+              np.tile(np.frombuffer(b"ab", np.uint8), 40_000), rng.integers(0, 2, 1023, dtype=np.uint8),
+              rng.integers(0, 2, 1024, dtype=np.uint8), rng.integers(0, 2, 1025, dtype=np.uint8),
+              rng.integers(0, 256, 4097, dtype=np.uint8), synth.repetitive(3 << 20, 5, period=7, mutation_rate=1e-4)]
+    for t in texts:
+        t = N.as_u8(t)
+        u, pidx = ref.divbwt(t)
+        got = divsufsort.inverse_bwt(u, pidx)
+        rc, exp = ref.inverse_bwt(u, pidx)
+        assert rc == 0 and (got == t).all(), (t.size, pidx)
+        if t.size > 1:  # n == 1: the reference returns before writing U (utils.c:124)
+            assert (got == exp).all(), (t.size, pidx)
+        u2, pidx2 = divsufsort.bwt(t)
+        assert (divsufsort.inverse_bwt(u2, pidx2) == t).all()
+    # argument checks of utils.c:120-123, same return codes
+    one = np.zeros(4, np.uint8)
+    for n, idx in ((-1, 0), (4, -1), (4, 5), (4, 0)):
+        assert N.lib.gsa_inverse_bw_transform(N.ptr(one), N.ptr(one), None, n, idx) == -1
+        assert ref.lib.inverse_bw_transform(one.ctypes.data_as(C.POINTER(C.c_uint8)), one.ctypes.data_as(C.POINTER(C.c_uint8)), None, n, idx) == -1
+    assert N.lib.gsa_inverse_bw_transform(None, N.ptr(one), None, 4, 1) == -1
+    assert N.lib.gsa_inverse_bw_transform(N.ptr(one), N.ptr(one), None, 0, 0) == 0
+
+
 def test_tile_boundaries(port):
     """Sizes straddling the radix tile (4096), rebuild tile (2048) and vector widths."""
     rng = np.random.default_rng(7)
