@@ -323,7 +323,7 @@ def run_ours(args, rank, local_rank, world):
         "roofline": {
             "bound": "hbm", "kernel": "k_radix_pass (onesweep LSD pass, u64 key + u32 value)",
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
-            "traffic": 24.1 * pass_elems / max(1, pass_launches), "traffic_source": "ncu --set full: dram read+write = 24.1 B/element (profiles/r1)", "launches": int(pass_launches), "avg_launch_ms": pass_ms / max(1, pass_launches),
+            "traffic": 24.3 * pass_elems / max(1, pass_launches), "traffic_source": "ncu --set full: dram read+write = 24.3 B/element (profiles/r1/v5_pass_rep1G.details.txt)", "launches": int(pass_launches), "avg_launch_ms": pass_ms / max(1, pass_launches),
             "algorithmic_bytes_per_launch": 24.0 * pass_elems / max(1, pass_launches), "algorithmic_bytes_formula": "24 B x elements (8+4 read, 8+4 written)",
             "share_of_step": pass_ms / ms if ms > 0 else None,
             "whole_build": {"algorithmic_bytes": int(alg_bytes), "achieved": alg_bytes * args.steps / (ms / 1e3) / 1e9,
