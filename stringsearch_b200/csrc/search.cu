@@ -100,6 +100,7 @@ struct LsmArgs {
   int accumulate;  // keep the previous (start,len) unless strictly longer
   u64 *io_start;
   u32 *io_len;
+  u32 carry;  // 0: every comparison starts at byte 0 (GSA_NO_MATCH_CARRY, measurements only)
 };
 
 template <int G>
@@ -122,23 +123,28 @@ __global__ void __launch_bounds__(256) k_lsm(const LsmArgs a) {
   // sacabase lib.rs:75-98 on the window sa[lo .. lo+w).  (Requesting the SA entries of both
   // possible next windows ahead of the comparison was tried and does not pay: at 1 GiB the walk
   // is bound by the rate of random DRAM sector fetches, not by their latency.)
+  // The needle lies between the two ends of the window (end-inclusive once an end has been
+  // compared), so every suffix inside shares at least min(lm, rm) bytes with it, lm / rm being the
+  // common prefix lengths found at the ends: comparisons start there instead of at byte 0 -- the
+  // lmatch / rmatch of libdivsufsort's sa_search (utils.c:275-286), which matters for long needles.
   u64 lo = 0, w = a.n;
+  u32 lm = 0, rm = 0;
   for (;;) {
     const bool act = have && w > 2;
     if (!__any_sync(0xffffffffu, act)) break;
     const u64 mid = w >> 1;
     const u64 s = act ? (u64)(u32)__ldg(a.sa + lo + mid) : 0;
-    const CmpResult c = group_compare<G>(a.text, s, a.n, pat, m, pw0, 0, act);
+    const CmpResult c = group_compare<G>(a.text, s, a.n, pat, m, pw0, a.carry ? min(lm, rm) : 0u, act);
     if (act) {
-      if (c.gt) { lo += mid; w -= mid; } else { w = mid + 1; }
+      if (c.gt) { lo += mid; w -= mid; lm = c.cpl; } else { w = mid + 1; rm = c.cpl; }
     }
   }
   u64 start = have ? (u64)(u32)__ldg(a.sa + lo) : 0;
-  u32 len = group_compare<G>(a.text, start, a.n, pat, m, pw0, 0, have).cpl;
+  u32 len = group_compare<G>(a.text, start, a.n, pat, m, pw0, a.carry ? min(lm, rm) : 0u, have).cpl;
   {
     const bool two = have && w == 2;
     const u64 s1 = two ? (u64)(u32)__ldg(a.sa + lo + 1) : 0;
-    const u32 y = group_compare<G>(a.text, s1, a.n, pat, m, pw0, 0, two).cpl;
+    const u32 y = group_compare<G>(a.text, s1, a.n, pat, m, pw0, a.carry ? min(lm, rm) : 0u, two).cpl;
     if (two && !(len > y)) { start = s1; len = y; }  // `x > y` keeps the first, ties go to the second
   }
   {
@@ -164,6 +170,7 @@ struct SearchAllArgs {
   u64 Q;
   i32 *left;
   i32 *count;
+  u32 carry;
 };
 
 template <int G>
@@ -189,17 +196,20 @@ __global__ void __launch_bounds__(256) k_search_all(const SearchAllArgs a) {
   // lower bound L: suffixes with r < 0 (suffix < pattern); upper bound U: suffixes with r <= 0
   // (suffix < pattern, or pattern is a prefix of it).  The two binary searches are independent
   // and are advanced together, so their memory round trips overlap.
+  // Each search carries the common prefix lengths found at its two bounds (sa_search's lmatch /
+  // rmatch, utils.c:275-286): a comparison starts at their minimum.
   u64 lo = 0, hi = a.n, lo2 = 0, hi2 = a.n;
+  u32 lm1 = 0, rm1 = 0, lm2 = 0, rm2 = 0;
   for (;;) {
     const bool act1 = have && lo < hi, act2 = have && lo2 < hi2;
     if (!__any_sync(0xffffffffu, act1 || act2)) break;
     const u64 mid1 = (lo + hi) >> 1, mid2 = (lo2 + hi2) >> 1;
     const u64 s1 = act1 ? (u64)(u32)__ldg(a.sa + mid1) : 0;
     const u64 s2 = act2 ? (u64)(u32)__ldg(a.sa + mid2) : 0;
-    const CmpResult c1 = group_compare<G>(a.text, s1, a.n, pat, m, pw0, 0, act1);
-    const CmpResult c2 = group_compare<G>(a.text, s2, a.n, pat, m, pw0, 0, act2);
-    if (act1) { if (c1.gt) lo = mid1 + 1; else hi = mid1; }
-    if (act2) { if (!c2.lt) lo2 = mid2 + 1; else hi2 = mid2; }
+    const CmpResult c1 = group_compare<G>(a.text, s1, a.n, pat, m, pw0, a.carry ? min(lm1, rm1) : 0u, act1);
+    const CmpResult c2 = group_compare<G>(a.text, s2, a.n, pat, m, pw0, a.carry ? min(lm2, rm2) : 0u, act2);
+    if (act1) { if (c1.gt) { lo = mid1 + 1; lm1 = c1.cpl; } else { hi = mid1; rm1 = c1.cpl; } }
+    if (act2) { if (!c2.lt) { lo2 = mid2 + 1; lm2 = c2.cpl; } else { hi2 = mid2; rm2 = c2.cpl; } }
   }
   const u64 left = lo;
   lo = lo2;
@@ -232,7 +242,7 @@ int lsm_device(const TextView &tv, const u8 *d_pats, const u64 *d_pat_off, u64 Q
                int accumulate, u64 *d_io_start, u32 *d_io_len, cudaStream_t st) {
   if (Q == 0) return GSA_OK;
   if (tv.n == 0) return GSA_EPANIC;  // sacabase lib.rs:89-91 indexes sa[0]
-  LsmArgs a{tv.text, tv.sa, tv.n, tv.text_avail, d_pats, d_pat_off, Q, offset, accumulate, d_io_start, d_io_len};
+  LsmArgs a{tv.text, tv.sa, tv.n, tv.text_avail, d_pats, d_pat_off, Q, offset, accumulate, d_io_start, d_io_len, getenv("GSA_NO_MATCH_CARRY") ? 0u : 1u};
   const int G = group_lanes(max_pat_len);
   const u64 warps = div_up(Q, 32 / G);
   const unsigned blocks = (unsigned)div_up(warps * 32, 256);
@@ -246,7 +256,7 @@ int lsm_device(const TextView &tv, const u8 *d_pats, const u64 *d_pat_off, u64 Q
 int search_all_device(const TextView &tv, const u8 *d_pats, const u64 *d_pat_off, u64 Q, u32 max_pat_len, i32 *d_left,
                       i32 *d_count, cudaStream_t st) {
   if (Q == 0) return GSA_OK;
-  SearchAllArgs a{tv.text, tv.sa, tv.n, d_pats, d_pat_off, Q, d_left, d_count};
+  SearchAllArgs a{tv.text, tv.sa, tv.n, d_pats, d_pat_off, Q, d_left, d_count, getenv("GSA_NO_MATCH_CARRY") ? 0u : 1u};
   const int G = group_lanes(max_pat_len);
   const u64 warps = div_up(Q, 32 / G);
   const unsigned blocks = (unsigned)div_up(warps * 32, 256);

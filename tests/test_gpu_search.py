@@ -93,6 +93,40 @@ def test_lsm_and_search_all_match_oracle(port, sigma, n, max_len):
     assert (sa.contains_batch(pats) == (ecnt > 0)).all()
 
 
+@pytest.mark.parametrize("kind", ["repetitive", "binary", "one_symbol"])
+def test_long_patterns_with_carried_match_lengths(port, kind):
+    """Needles of up to 5000 bytes on texts with long repeats: the comparisons start at
+    min(lmatch, rmatch) (sa_search, utils.c:275-286) and must give the oracle's answers."""
+    from stringsearch_b200 import synth
+
+    rng = np.random.default_rng(len(kind))
+    if kind == "repetitive":
+        t = synth.repetitive(200_000, 9, period=700, mutation_rate=2e-3)
+    elif kind == "binary":
+        t = np.tile(rng.integers(0, 2, 5000, dtype=np.uint8), 30)
+        t[rng.integers(0, t.size, 40)] ^= 1
+    else:
+        t = np.zeros(20_000, np.uint8)
+    sa = _index(t, port)
+    pats = _mixed_patterns(t, rng, 600, 5000)
+    # long substrings with one mutation somewhere inside, and exact long substrings
+    for i in range(200):
+        o = int(rng.integers(0, t.size - 10))
+        m = int(rng.integers(200, 5000))
+        b = bytearray(t[o:o + m].tobytes())
+        if i % 2 and b:
+            b[int(rng.integers(0, len(b)))] ^= 1
+        pats.append(bytes(b))
+    s, l = sa.longest_substring_match_batch(pats)
+    es, el = port.lsm_batch(t, sa.sa, pats)
+    bad = np.flatnonzero((s != es) | (l != el))
+    assert bad.size == 0, (bad[:5], s[bad[:3]], es[bad[:3]], l[bad[:3]], el[bad[:3]])
+    left, cnt = sa.search_all_batch(pats)
+    eleft, ecnt = port.search_all_batch(t, sa.sa, pats)
+    bad = np.flatnonzero((left != eleft) | (cnt != ecnt))
+    assert bad.size == 0, (bad[:5], left[bad[:3]], eleft[bad[:3]], cnt[bad[:3]], ecnt[bad[:3]])
+
+
 def test_search_edge_cases(port):
     from stringsearch_b200 import divsufsort, sacabase
 
