@@ -28,11 +28,44 @@ extern "C" {
     fn gsa_part_num_partitions(p: *const GsaPart) -> u64;
     fn gsa_part_lsm_batch(p: *mut GsaPart, pats: *const u8, pat_off: *const u64, q: u64, out_start: *mut u64, out_len: *mut u32) -> i32;
     fn gsa_part_destroy(p: *mut GsaPart);
+    fn gsa_divbwt(T: *const u8, U: *mut u8, A: *mut i32, n: i32) -> i32;
+    fn gsa_inverse_bw_transform(T: *const u8, U: *mut u8, A: *mut i32, n: i32, idx: i32) -> i32;
+    fn gsa_lcp(T: *const u8, SA: *const i32, LCP: *mut i32, n: i32, device: i32) -> i32;
     fn gsa_last_error() -> *const c_char;
 }
 
 fn last_error() -> String {
     unsafe { std::ffi::CStr::from_ptr(gsa_last_error()).to_string_lossy().into_owned() }
+}
+
+/// Burrows-Wheeler transform with libdivsufsort's `divbwt` convention (divsufsort.c:372-405):
+/// returns the transformed string and the primary index.
+pub fn bwt(text: &[u8]) -> (Vec<u8>, i32) {
+    assert!(text.len() < i32::max_value() as usize);
+    let mut u = vec![0u8; text.len()];
+    let ret = unsafe { gsa_divbwt(text.as_ptr(), u.as_mut_ptr(), std::ptr::null_mut(), text.len() as i32) };
+    assert!(ret >= 0, "{}", last_error());
+    (u, ret)
+}
+
+/// Inverse of [`bwt`] (`inverse_bw_transform`, utils.c:111-156).
+pub fn inverse_bwt(u: &[u8], primary_index: i32) -> Vec<u8> {
+    let mut t = vec![0u8; u.len()];
+    let ret = unsafe { gsa_inverse_bw_transform(u.as_ptr(), t.as_mut_ptr(), std::ptr::null_mut(), u.len() as i32, primary_index) };
+    assert_eq!(0, ret, "{}", last_error());
+    t
+}
+
+/// LCP array of a suffix array: `lcp[0] = 0`, `lcp[j]` = common prefix length of the suffixes
+/// at `sa[j-1]` and `sa[j]`.
+pub fn lcp(text: &[u8], sa: &[i32]) -> Vec<i32> {
+    assert_eq!(text.len(), sa.len(), "text and suffix array should have same len");
+    let mut out = vec![0i32; sa.len()];
+    if !sa.is_empty() {
+        let ret = unsafe { gsa_lcp(text.as_ptr(), sa.as_ptr(), out.as_mut_ptr(), sa.len() as i32, 0) };
+        assert_eq!(0, ret, "{}", last_error());
+    }
+    out
 }
 
 /// Sort suffixes of `text` and store their lexographic order in the given suffix array `sa`.

@@ -5,6 +5,8 @@
 #include <cassert>
 #include <cstdio>
 #include <string>
+#include <utility>
+#include <vector>
 
 #include "divsufsort.hpp"
 #include "sacapart.hpp"
@@ -52,6 +54,22 @@ int main() {
     auto b = divsufsort::sort(banana);
     CHECK((b.search_all("ana") == std::vector<int32_t>{3, 1}));
     CHECK(b.contains("nan") && !b.contains("nab"));
+  }
+  {  // BWT round trip and LCP (divsufsort.c:372-405, utils.c:111-156; lcp.cu)
+    const std::string banana = "banana";
+    const auto *bt = reinterpret_cast<const uint8_t *>(banana.data());
+    auto tr = divsufsort::bwt(bt, banana.size());
+    CHECK(std::string(tr.first.begin(), tr.first.end()) == "annbaa" && tr.second == 4);
+    auto back = divsufsort::inverse_bwt(tr.first.data(), tr.first.size(), tr.second);
+    CHECK(std::string(back.begin(), back.end()) == banana);
+    auto b = divsufsort::sort(banana);
+    CHECK((divsufsort::lcp(bt, banana.size(), b.sa().data()) == std::vector<int32_t>{0, 1, 3, 0, 0, 2}));
+    std::string big;
+    for (int i = 0; i < 50000; ++i) big += "abracadabra"[(i * 7 + i / 13) % 11];
+    const auto *gt = reinterpret_cast<const uint8_t *>(big.data());
+    auto tr2 = divsufsort::bwt(gt, big.size());
+    auto back2 = divsufsort::inverse_bwt(tr2.first.data(), tr2.first.size(), tr2.second);
+    CHECK(std::string(back2.begin(), back2.end()) == big);
   }
   {  // panics
     bool threw = false;
