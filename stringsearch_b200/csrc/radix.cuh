@@ -124,7 +124,8 @@ template <int THREADS, int IPT>
 struct PassCfg {
   static constexpr int WARPS = THREADS / 32;
   static constexpr int TILE = THREADS * IPT;
-  static constexpr size_t SMEM = (size_t)TILE * 8 + (size_t)TILE * 4 + (size_t)WARPS * RADIX * 4 + RADIX * 4 + RADIX * 4;
+  // keys, values, per-warp digit counts (u16: a warp holds at most 32 * IPT elements, a tile offset is below TILE), bin offsets
+  static constexpr size_t SMEM = (size_t)TILE * 8 + (size_t)TILE * 4 + (size_t)WARPS * RADIX * 2 + RADIX * 4;
 };
 
 // Lanes of the warp whose 8-bit digit equals mine, from 8 ballots (cost independent of the
@@ -143,21 +144,20 @@ __device__ __forceinline__ u32 peers_by_ballot(u32 d) {
 template <int THREADS, int IPT, bool GEN, int MIN_BLOCKS = 3>
 __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_radix_pass(const PassArgs a) {
   static_assert(THREADS >= RADIX && THREADS % 32 == 0, "one thread per bin is assumed");
-  static_assert(IPT % 2 == 0 && 32 * IPT <= 65535, "warp-local ranks are packed as u16 pairs");
+  static_assert(IPT % 2 == 0 && THREADS * IPT <= 65535, "ranks, counts and tile offsets are kept as u16");
   constexpr int WARPS = THREADS / 32;
   constexpr int TILE = THREADS * IPT;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   u64 *skeys = reinterpret_cast<u64 *>(smem_raw);          // [TILE]
   u32 *svals = reinterpret_cast<u32 *>(skeys + TILE);      // [TILE]
-  u32 *whist = svals + TILE;                               // [WARPS][256] counts -> offsets
-  u32 *bin_excl = whist + WARPS * RADIX;                   // [256] tile-local exclusive offset of each bin
-  u32 *bin_gofs = bin_excl + RADIX;                        // [256] global offset - local offset
+  u16 *whist = reinterpret_cast<u16 *>(svals + TILE);      // [WARPS][256] counts -> tile offsets, two per 32-bit word
+  u32 *bin_gofs = reinterpret_cast<u32 *>(whist + WARPS * RADIX);  // [256] global offset - local offset
   __shared__ u32 s_tile;
   __shared__ u32 s_wsum[RADIX / 32];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) s_tile = atomicAdd(a.counter, 1u);
-  for (int i = tid; i < WARPS * RADIX; i += THREADS) whist[i] = 0;
+  for (int i = tid; i < WARPS * RADIX / 2; i += THREADS) reinterpret_cast<u32 *>(whist)[i] = 0;
   __syncthreads();
   const u32 tile = s_tile;
   const u32 tile_base = tile * (u32)TILE;
@@ -192,14 +192,15 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_radix_pass(const PassAr
   // (match.any's cost grows with the number of distinct values) and from 8 ballots otherwise.
   u32 lrank[IPT / 2];  // two u16 per register
   const u32 lt = lanemask_lt();
-  u32 *wh = whist + warp * RADIX;
+  u16 *wh = whist + warp * RADIX;
+  u32 *wh32 = reinterpret_cast<u32 *>(wh);  // shared-memory atomics work on the 32-bit word holding the bin's half
   bool use_match;
   {
     const u32 d = (u32)(key[0] >> a.shift) & 255u;
     const u32 peers = peers_by_ballot(d);
     const u32 below = __popc(peers & lt);
     u32 base = 0;
-    if (below == 0) base = atomicAdd(&wh[d], (u32)__popc(peers));
+    if (below == 0) base = (atomicAdd(&wh32[d >> 1], (u32)__popc(peers) << (16u * (d & 1u))) >> (16u * (d & 1u))) & 0xffffu;
     base = __shfl_sync(0xffffffffu, base, __ffs(peers) - 1);
     lrank[0] = base + below;
     use_match = __popc(__ballot_sync(0xffffffffu, below == 0)) <= 6;
@@ -211,7 +212,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_radix_pass(const PassAr
       const u32 peers = __match_any_sync(0xffffffffu, d);
       const u32 below = __popc(peers & lt);
       u32 base = 0;
-      if (below == 0) base = atomicAdd(&wh[d], (u32)__popc(peers));
+      if (below == 0) base = (atomicAdd(&wh32[d >> 1], (u32)__popc(peers) << (16u * (d & 1u))) >> (16u * (d & 1u))) & 0xffffu;
       base = __shfl_sync(0xffffffffu, base, __ffs(peers) - 1);
       if (k & 1) lrank[k >> 1] |= (base + below) << 16; else lrank[k >> 1] = base + below;
     }
@@ -222,7 +223,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_radix_pass(const PassAr
       const u32 peers = peers_by_ballot(d);
       const u32 below = __popc(peers & lt);
       u32 base = 0;
-      if (below == 0) base = atomicAdd(&wh[d], (u32)__popc(peers));
+      if (below == 0) base = (atomicAdd(&wh32[d >> 1], (u32)__popc(peers) << (16u * (d & 1u))) >> (16u * (d & 1u))) & 0xffffu;
       base = __shfl_sync(0xffffffffu, base, __ffs(peers) - 1);
       if (k & 1) lrank[k >> 1] |= (base + below) << 16; else lrank[k >> 1] = base + below;
     }
@@ -230,12 +231,12 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_radix_pass(const PassAr
   __syncthreads();
 
   // ---- bin totals, per-warp offsets, exclusive scan over bins; publish the aggregate ----
-  u32 cnt = 0, pub = 0;
+  u32 cnt = 0, pub = 0, bin_ex = 0;
   if (tid < RADIX) {
 #pragma unroll
     for (int w = 0; w < WARPS; ++w) {
       const u32 c = whist[w * RADIX + tid];
-      whist[w * RADIX + tid] = cnt;
+      whist[w * RADIX + tid] = (u16)cnt;
       cnt += c;
     }
     pub = cnt - ((tid == RADIX - 1) ? ((u32)TILE - valid) : 0u);  // padding is not data
@@ -256,10 +257,9 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_radix_pass(const PassAr
   if (tid < RADIX) {
     u32 add = 0;
     for (int i = 0; i < warp; ++i) add += s_wsum[i];
-    const u32 ex = cnt + add;
-    bin_excl[tid] = ex;
+    const u32 ex = bin_ex = cnt + add;  // tile-local exclusive offset of the bin (= the offset of warp 0 after this step)
 #pragma unroll
-    for (int w = 0; w < WARPS; ++w) whist[w * RADIX + tid] += ex;
+    for (int w = 0; w < WARPS; ++w) whist[w * RADIX + tid] = (u16)(whist[w * RADIX + tid] + ex);
   }
   __syncthreads();
 
@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_radix_pass(const PassAr
       }
       st_volatile_u32(a.status + (size_t)tile * RADIX + tid, st_pre(excl + pub));
     }
-    bin_gofs[tid] = a.bin_base[tid] + excl - bin_excl[tid];
+    bin_gofs[tid] = a.bin_base[tid] + excl - bin_ex;
   }
   __syncthreads();
 

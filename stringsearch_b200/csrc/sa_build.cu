@@ -1261,6 +1261,10 @@ namespace {
 constexpr int PASS_THREADS = 256;
 constexpr int PASS_IPT = 16;
 constexpr int PASS_TILE = PASS_THREADS * PASS_IPT;
+#ifndef GSA_PASS_MIN_BLOCKS
+#define GSA_PASS_MIN_BLOCKS 3
+#endif
+constexpr int PASS_MIN_BLOCKS = GSA_PASS_MIN_BLOCKS;  // resident CTAs per SM the pass kernel is compiled for
 constexpr int RB_THREADS = 512;
 constexpr int RB_IPT = 8;
 constexpr int RB_TILE = RB_THREADS * RB_IPT;
@@ -1423,7 +1427,7 @@ static int run_passes(const Layout &y, u32 L, int npass, int cur, const KeyGen *
       } else if (pass_cfg == 3) {
         k_radix_pass<512, 12, false, 2><<<(u32)div_up(L, 512 * 12), 512, PassCfg<512, 12>::SMEM, st>>>(a);
       } else {
-        k_radix_pass<PASS_THREADS, PASS_IPT, false><<<tiles, PASS_THREADS, smem, st>>>(a);
+        k_radix_pass<PASS_THREADS, PASS_IPT, false, PASS_MIN_BLOCKS><<<tiles, PASS_THREADS, smem, st>>>(a);
       }
       cur ^= 1;
     }
@@ -1451,7 +1455,7 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
     // opt in to > 48 KB dynamic shared memory (idempotent, per device)
     const int smem = (int)PassCfg<PASS_THREADS, PASS_IPT>::SMEM;
     GSA_TRY(cudaFuncSetAttribute(k_radix_pass<PASS_THREADS, PASS_IPT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    GSA_TRY(cudaFuncSetAttribute(k_radix_pass<PASS_THREADS, PASS_IPT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    GSA_TRY(cudaFuncSetAttribute(k_radix_pass<PASS_THREADS, PASS_IPT, false, PASS_MIN_BLOCKS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     GSA_TRY(cudaFuncSetAttribute(k_radix_pass<256, 12, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PassCfg<256, 12>::SMEM));
     GSA_TRY(cudaFuncSetAttribute(k_radix_pass<384, 16, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PassCfg<384, 16>::SMEM));
     GSA_TRY(cudaFuncSetAttribute(k_radix_pass<512, 12, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PassCfg<512, 12>::SMEM));
