@@ -502,6 +502,8 @@ struct PatternsOnDevice {
     const u64 bytes = h_off[Q];
     GSA_TRY_RC(pats.alloc((size_t)bytes + 64));
     GSA_TRY_RC(off.alloc((size_t)Q + 1));
+    // the kernels read whole aligned words: the bytes behind the last pattern are defined (masked out, never compared)
+    GSA_TRY(cudaMemsetAsync(pats.p + bytes, 0, 64, st));
     if (bytes) GSA_TRY(cudaMemcpyAsync(pats.p, h_pats, (size_t)bytes, cudaMemcpyHostToDevice, st));
     GSA_TRY(cudaMemcpyAsync(off.p, h_off, (size_t)(Q + 1) * sizeof(u64), cudaMemcpyHostToDevice, st));
     return GSA_OK;

@@ -217,12 +217,31 @@ constexpr u32 RANK_MASK = 0x7fffffffu;
 // small, or unique) is decided once per round by k_huge_prepare and published in STATE; every
 // reader of a huge label resolves it through STATE, members rewrite their own rank on the fly.
 constexpr u32 HUGE_M = 256;
-constexpr u32 HUGE_T = 1u << 16;
+// Smallest group that is handled through the group tables.  The tables are indexed by label / HUGE_M, so
+// 2 * HUGE_M is the floor.  Measured (tools/shapes_bench.py, 256 MiB): 65536 -> 512 changes nothing on
+// rep_1G, zeros, period-7 text, but a text whose groups have a few thousand members (period 100 000,
+// 2684 repeats) drops from 308 ms to 86 ms: those groups were sorted in full in every round.
+#ifndef GSA_HUGE_T
+#define GSA_HUGE_T 512
+#endif
+constexpr u32 HUGE_T = GSA_HUGE_T;
 static_assert(HUGE_T >= 2 * HUGE_M, "a huge range must hold two candidate labels");
 constexpr u32 STATE_FINAL = 0x80000000u;
 constexpr u32 HUGE_REPS = 8;  // representatives per huge group: rho* is the plurality of their second key halves
 
 __device__ __forceinline__ bool is_huge_label(u32 lab) { return (lab & (HUGE_M - 1u)) == 0u; }
+// Representatives are kept as 64-bit keys  (255 - round) << 56 | hash << 32 | suffix  and updated with
+// atomicMin: a slot holds the member with the smallest hash among the volunteers of the newest round.
+// That makes the choice independent of the order in which blocks run (with plain stores the last
+// writer wins, i.e. always a member from the end of the text -- on a^n exactly the members that
+// turn into the minority one round later).  All ones = empty.
+__device__ __forceinline__ u64 rep_key(u32 round, u32 hash24, u32 sufx) {
+  return ((u64)(255u - round) << 56) | ((u64)(hash24 & 0xffffffu) << 32) | sufx;
+}
+__device__ __forceinline__ u32 mix32(u32 x) {
+  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+  return x;
+}
 
 // The BAG.  A suffix whose group has at most TINY_MAX members leaves the text-order walk and
 // the radix sort for good: such groups are kept, group by group, as (suffix, slot) entries in
@@ -314,12 +333,14 @@ __global__ void __launch_bounds__(256) k_rank_huge0(const KeyGen g, const HugeKe
 // Once per round, one thread per huge group: classify it, publish the verdict in STATE for the
 // readers of this round, and rebuild the list of huge groups.
 __global__ void __launch_bounds__(256) k_huge_prepare(const u32 *__restrict__ hin, u32 cnt, u64 *__restrict__ G,
-                                                      u64 *__restrict__ state, u32 *__restrict__ rep, u32 round,
+                                                      u64 *__restrict__ state, u64 *__restrict__ rep, u32 round,
                                                       u32 tiny_max, u32 *__restrict__ hout, u32 *__restrict__ hout_count,
-                                                      u32 *__restrict__ verdicts) {
+                                                      u32 *__restrict__ verdicts, u32 *__restrict__ seen) {
   const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= cnt) return;
   const u32 lab = hin[j];
+  // a group that was sorted in full (no rho*) and did not split is appended again by the rebuild: keep one entry
+  if (seen != nullptr && atomicExch(seen + lab / HUGE_M, round) == round) return;
   const u64 g = G[lab];
   const i64 gs = (i64)(i32)(u32)g, ge = (i64)(i32)(u32)(g >> 32);
   const i64 size = ge - gs + 1;
@@ -350,7 +371,7 @@ __global__ void __launch_bounds__(256) k_huge_prepare(const u32 *__restrict__ hi
 // of the group.
 __global__ void __launch_bounds__(256) k_huge_rho(const u32 *__restrict__ hl, const u32 *__restrict__ hl_count,
                                                   const u32 *__restrict__ rank, const u64 *__restrict__ state,
-                                                  const u32 *__restrict__ rep, u64 *__restrict__ rho, u32 round, u64 h,
+                                                  const u64 *__restrict__ rep, u64 *__restrict__ rho, u32 round, u64 h,
                                                   u32 n) {
   const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= *hl_count) return;
@@ -358,7 +379,7 @@ __global__ void __launch_bounds__(256) k_huge_rho(const u32 *__restrict__ hl, co
   u32 val[HUGE_REPS];
   u32 nv = 0;
   for (u32 x = 0; x < HUGE_REPS; ++x) {
-    const u32 r = rep[(lab / HUGE_M) * HUGE_REPS + x];
+    const u32 r = (u32)rep[(lab / HUGE_M) * HUGE_REPS + x];
     if (r >= n) continue;
     bool fin;
     const u32 w = rank[r];
@@ -397,7 +418,7 @@ struct GatherArgs {
   const u64 *state;   // [n / HUGE_M + 2] verdicts of k_huge_prepare, tagged with the round
   const u32 *verdicts;  // [1] != 0: some huge group got a verdict this round (else STATE need not be read)
   const u64 *rho;     // [n / HUGE_M + 2] round << 32 | rho*  (k_huge_rho)
-  u32 *rep;           // [n / HUGE_M + 2][HUGE_REPS] members of every huge group, refreshed from the inert ones
+  u64 *rep;           // [n / HUGE_M + 2][HUGE_REPS] members of every huge group (rep_key), refreshed from the inert ones
   u64 *keys_out;
   u32 *vals_out;
   u32 *lst_out;
@@ -509,8 +530,12 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_gather(const GatherArgs
         const u64 e = tb[k];
         if ((u32)(e >> 32) == a.round && (u32)e == r2[k]) {
           so = false;  // inert: shares the group's dominant key
-          // a few of them per round volunteer as next round's representative
-          if (k == 0 && chunk == blockIdx.x) a.rep[(w[k] / HUGE_M) * HUGE_REPS + ((blockIdx.x + warp) % HUGE_REPS)] = sfx[k];
+          // one in 256 of them volunteers as a representative of its group for the next round
+          if (((sfx[k] * 0x9e3779b1u) >> 24) == (a.round & 0xffu)) {  // cheap 1-in-256 pre-filter
+            const u32 hsh = mix32(sfx[k] ^ (a.round * 0x9e3779b9u));
+            atomicMin(reinterpret_cast<unsigned long long *>(a.rep + (w[k] / HUGE_M) * HUGE_REPS + ((hsh >> 8) & (HUGE_REPS - 1u))),
+                      (unsigned long long)rep_key(a.round, hsh >> 11, sfx[k]));
+          }
         }
       }
       const u64 kx = so ? (((u64)w[k] << a.lab_bits) | r2[k]) : 0ull;
@@ -789,7 +814,8 @@ struct RebuildArgs {
   u64 *G;              // [n + 2] slot range of every live group, indexed by its label
   u32 *hlist;          // labels of the huge groups created in this round are appended here
   u32 *hcount;
-  u32 *rep;            // [n / HUGE_M + 2] their first member becomes the representative
+  u64 *rep;            // [n / HUGE_M + 2][HUGE_REPS] their first member becomes the representative
+  u32 round;           // round this rebuild belongs to (0 = round 0)
   HugeKeyTable hkt;    // round 0: huge groups register their key here (k_rank_huge0 labels the members)
   u32 tiny_max;        // groups of at most this many suffixes move to the bag (0: no bag)
   u64 *bag_desc;       // (first slot | size << 32) of every tiny group formed by this rebuild
@@ -1085,7 +1111,7 @@ __global__ void __launch_bounds__(THREADS, 2) k_rebuild(const RebuildArgs a) {
             a.G[lab] = (u64)(s1 - 1u) | ((u64)(e1 - 1u) << 32);
             if (!keep && is_huge_label(lab)) {
               a.hlist[atomicAdd(a.hcount, 1u)] = lab;
-              a.rep[(lab / HUGE_M) * HUGE_REPS] = sx[j + 1];  // the other slots are filled by inert volunteers
+              a.rep[(lab / HUGE_M) * HUGE_REPS] = rep_key(a.round + 1u, 0u, sx[j + 1]);  // the other slots are filled by inert volunteers
               if (ROUND0) hkt_insert(a.hkt, kx[j + 1], lab);
             }
           }
@@ -1277,7 +1303,8 @@ struct Layout {
   u64 *packed; u64 packed_words;
   u64 *keys[2]; u32 *vals[2]; u32 *slots; u32 *lst[2]; u32 *rank;
   u64 *G;                      // [n + 2] slot range of every live group, indexed by label
-  u64 *state, *rho; u32 *rep;  // [n / HUGE_M + 2] per huge label
+  u64 *state, *rho, *rep;      // [n / HUGE_M + 2] per huge label (rep: HUGE_REPS entries each)
+  u32 *seen;                   // [n / HUGE_M + 2] round in which k_huge_prepare last saw the label
   u64 *hkt_keys; u32 *hkt_labels; u32 hkt_cap;  // round-0 key -> label of the huge groups
   u32 *hfull;                  // [256] window histogram of round 0
   u32 *hlist[2]; u32 hcap;     // labels of the huge groups
@@ -1309,7 +1336,8 @@ Layout make_layout(char *base, u32 n) {
   y.G = c.take<u64>(N + 2);
   y.state = c.take<u64>(N / HUGE_M + 2);
   y.rho = c.take<u64>(N / HUGE_M + 2);
-  y.rep = c.take<u32>((N / HUGE_M + 2) * HUGE_REPS);
+  y.rep = c.take<u64>((N / HUGE_M + 2) * HUGE_REPS);
+  y.seen = c.take<u32>(N / HUGE_M + 2);
   y.hkt_cap = 1024;
   while (y.hkt_cap < 4 * (N / HUGE_T + 1)) y.hkt_cap <<= 1;
   y.hkt_keys = c.take<u64>(y.hkt_cap);
@@ -1588,8 +1616,9 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
   int hcur = 0;  // hlist[hcur] / hcount[hcur]: huge groups entering the next round
   GSA_TRY(cudaMemsetAsync(y.state, 0, ((size_t)n / HUGE_M + 2) * sizeof(u64), st));
   GSA_TRY(cudaMemsetAsync(y.rho, 0, ((size_t)n / HUGE_M + 2) * sizeof(u64), st));
+  GSA_TRY(cudaMemsetAsync(y.seen, 0, ((size_t)n / HUGE_M + 2) * sizeof(u32), st));
   GSA_TRY(cudaMemsetAsync(y.hcount, 0, 2 * sizeof(u32), st));
-  GSA_TRY(cudaMemsetAsync(y.rep, 0xff, ((size_t)n / HUGE_M + 2) * HUGE_REPS * sizeof(u32), st));
+  GSA_TRY(cudaMemsetAsync(y.rep, 0xff, ((size_t)n / HUGE_M + 2) * HUGE_REPS * sizeof(u64), st));
   // tail summaries + survivor count, then the rebuild proper.  *survivors_out is known before the
   // rebuild is launched, which lets the last round skip its rank writes.
   // The bag is off in sparse mode (most suffixes then carry no label at all).
@@ -1597,7 +1626,7 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
   if (const char *e = getenv("GSA_TINY_MAX")) tiny_conf = std::min<u32>(TINY_MAX, (u32)atoi(e));
   int bcur = 0;  // bag buffer the rebuild of the current round appends to (= input of the next round)
   GSA_TRY(cudaMemsetAsync(y.bag_count, 0, 4 * sizeof(u32), st));
-  auto launch_rebuild = [&](bool round0, u32 L, int kv, bool may_finish, u32 *survivors_out) -> int {
+  auto launch_rebuild = [&](bool round0, u32 rnd, u32 L, int kv, bool may_finish, u32 *survivors_out) -> int {
     const u32 tiles = (u32)div_up(L, RB_TILE);
     GSA_TRY(cudaMemsetAsync(y.survivors, 0, sizeof(u32), st));
     RebuildArgs r;
@@ -1607,7 +1636,7 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
     r.short_from = round0 ? (n - ns) : 0xffffffffu;
     r.lab_bits = lab_bits;
     r.rank = y.rank; r.SA = d_SA;
-    r.G = y.G; r.hlist = y.hlist[hcur]; r.hcount = y.hcount + hcur; r.rep = y.rep;
+    r.G = y.G; r.hlist = y.hlist[hcur]; r.hcount = y.hcount + hcur; r.rep = y.rep; r.round = rnd;
     r.hkt = HugeKeyTable{y.hkt_keys, y.hkt_labels, y.hkt_cap - 1};
     r.survivors = y.survivors;
     r.tile_tail = y.tile_tail; r.next_tail = y.next_tail;
@@ -1652,7 +1681,7 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
 
   u32 survivors = 0;
   GSA_TRY(cudaMemsetAsync(y.hkt_labels, 0, (size_t)y.hkt_cap * sizeof(u32), st));
-  GSA_TRY_RC(launch_rebuild(true, n, cur, true, &survivors));
+  GSA_TRY_RC(launch_rebuild(true, 0, n, cur, true, &survivors));
   if (survivors >= HUGE_T) {  // there may be huge groups: label their members in text order
     const u32 blocks = (u32)std::min<u64>((u64)sms * 8, std::max<u64>(1, div_up(n, 256)));
     k_rank_huge0<<<blocks, 256, 0, st>>>(gen, HugeKeyTable{y.hkt_keys, y.hkt_labels, y.hkt_cap - 1}, n - ns, y.rank);
@@ -1698,7 +1727,7 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
     GSA_TRY(cudaMemsetAsync(y.hcount + (hcur ^ 1), 0, sizeof(u32), st));
     GSA_TRY(cudaMemsetAsync(y.hcount + 2, 0, sizeof(u32), st));
     if (hc) {
-      k_huge_prepare<<<(u32)div_up(hc, 256), 256, 0, st>>>(y.hlist[hcur], hc, y.G, y.state, y.rep, round, tiny_max, y.hlist[hcur ^ 1], y.hcount + (hcur ^ 1), y.hcount + 2);
+      k_huge_prepare<<<(u32)div_up(hc, 256), 256, 0, st>>>(y.hlist[hcur], hc, y.G, y.state, y.rep, round, tiny_max, y.hlist[hcur ^ 1], y.hcount + (hcur ^ 1), y.hcount + 2, getenv("GSA_NO_DEDUPE") ? nullptr : y.seen);
       KLAUNCH_CHECK();
       if (stats) stats->kernel_launches++;
     }
@@ -1787,7 +1816,7 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
         KLAUNCH_CHECK();
       }
       if (stats) stats->kernel_launches += 4;
-      GSA_TRY_RC(launch_rebuild(false, S, cur, Llive == S, &survivors));
+      GSA_TRY_RC(launch_rebuild(false, round, S, cur, Llive == S, &survivors));
     }
     GSA_TRY(cudaEventRecord(ev[3], st));
     u32 nbag_next = 0;
