@@ -227,7 +227,7 @@ constexpr u32 HUGE_M = 256;
 constexpr u32 HUGE_T = GSA_HUGE_T;
 static_assert(HUGE_T >= 2 * HUGE_M, "a huge range must hold two candidate labels");
 constexpr u32 STATE_FINAL = 0x80000000u;
-constexpr u32 HUGE_REPS = 8;  // representatives per huge group: rho* is the plurality of their second key halves
+constexpr u32 HUGE_REPS = 16;  // representatives per huge group: rho* is the plurality of their second key halves
 
 __device__ __forceinline__ bool is_huge_label(u32 lab) { return (lab & (HUGE_M - 1u)) == 0u; }
 // Representatives are kept as 64-bit keys  (255 - round) << 56 | hash << 32 | suffix  and updated with
@@ -1682,11 +1682,16 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
   u32 survivors = 0;
   GSA_TRY(cudaMemsetAsync(y.hkt_labels, 0, (size_t)y.hkt_cap * sizeof(u32), st));
   GSA_TRY_RC(launch_rebuild(true, 0, n, cur, true, &survivors));
-  if (survivors >= HUGE_T) {  // there may be huge groups: label their members in text order
-    const u32 blocks = (u32)std::min<u64>((u64)sms * 8, std::max<u64>(1, div_up(n, 256)));
-    k_rank_huge0<<<blocks, 256, 0, st>>>(gen, HugeKeyTable{y.hkt_keys, y.hkt_labels, y.hkt_cap - 1}, n - ns, y.rank);
-    KLAUNCH_CHECK();
-    if (stats) stats->kernel_launches++;
+  if (survivors >= HUGE_T) {  // there may be huge groups: if so, label their members in text order
+    u32 hc0 = 0;
+    GSA_TRY(cudaMemcpyAsync(&hc0, y.hcount + hcur, sizeof(u32), cudaMemcpyDeviceToHost, st));
+    GSA_TRY(cudaStreamSynchronize(st));
+    if (hc0) {
+      const u32 blocks = (u32)std::min<u64>((u64)sms * 8, std::max<u64>(1, div_up(n, 256)));
+      k_rank_huge0<<<blocks, 256, 0, st>>>(gen, HugeKeyTable{y.hkt_keys, y.hkt_labels, y.hkt_cap - 1}, n - ns, y.rank);
+      KLAUNCH_CHECK();
+      if (stats) stats->kernel_launches++;
+    }
   }
   GSA_TRY(cudaEventRecord(ev[3], st));
   u32 nbag = 0;  // entries of bag buffer bcur
