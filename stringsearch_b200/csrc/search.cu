@@ -103,7 +103,9 @@ struct LsmArgs {
   u32 carry;  // 0: every comparison starts at byte 0 (GSA_NO_MATCH_CARRY, measurements only)
 };
 
-template <int G>
+// CARRY: start comparisons at min(lmatch, rmatch); pointless (and measurably slower in k_search_all)
+// when every needle fits one comparison step of the group (4 * G bytes).
+template <int G, bool CARRY>
 __global__ void __launch_bounds__(256) k_lsm(const LsmArgs a) {
   constexpr int PER_WARP = 32 / G;
   const u32 lane = lane_id();
@@ -134,17 +136,17 @@ __global__ void __launch_bounds__(256) k_lsm(const LsmArgs a) {
     if (!__any_sync(0xffffffffu, act)) break;
     const u64 mid = w >> 1;
     const u64 s = act ? (u64)(u32)__ldg(a.sa + lo + mid) : 0;
-    const CmpResult c = group_compare<G>(a.text, s, a.n, pat, m, pw0, a.carry ? min(lm, rm) : 0u, act);
+    const CmpResult c = group_compare<G>(a.text, s, a.n, pat, m, pw0, CARRY ? min(lm, rm) : 0u, act);
     if (act) {
       if (c.gt) { lo += mid; w -= mid; lm = c.cpl; } else { w = mid + 1; rm = c.cpl; }
     }
   }
   u64 start = have ? (u64)(u32)__ldg(a.sa + lo) : 0;
-  u32 len = group_compare<G>(a.text, start, a.n, pat, m, pw0, a.carry ? min(lm, rm) : 0u, have).cpl;
+  u32 len = group_compare<G>(a.text, start, a.n, pat, m, pw0, CARRY ? min(lm, rm) : 0u, have).cpl;
   {
     const bool two = have && w == 2;
     const u64 s1 = two ? (u64)(u32)__ldg(a.sa + lo + 1) : 0;
-    const u32 y = group_compare<G>(a.text, s1, a.n, pat, m, pw0, a.carry ? min(lm, rm) : 0u, two).cpl;
+    const u32 y = group_compare<G>(a.text, s1, a.n, pat, m, pw0, CARRY ? min(lm, rm) : 0u, two).cpl;
     if (two && !(len > y)) { start = s1; len = y; }  // `x > y` keeps the first, ties go to the second
   }
   {
@@ -173,7 +175,7 @@ struct SearchAllArgs {
   u32 carry;
 };
 
-template <int G>
+template <int G, bool CARRY>
 __global__ void __launch_bounds__(256) k_search_all(const SearchAllArgs a) {
   constexpr int PER_WARP = 32 / G;
   const u32 lane = lane_id();
@@ -206,8 +208,8 @@ __global__ void __launch_bounds__(256) k_search_all(const SearchAllArgs a) {
     const u64 mid1 = (lo + hi) >> 1, mid2 = (lo2 + hi2) >> 1;
     const u64 s1 = act1 ? (u64)(u32)__ldg(a.sa + mid1) : 0;
     const u64 s2 = act2 ? (u64)(u32)__ldg(a.sa + mid2) : 0;
-    const CmpResult c1 = group_compare<G>(a.text, s1, a.n, pat, m, pw0, a.carry ? min(lm1, rm1) : 0u, act1);
-    const CmpResult c2 = group_compare<G>(a.text, s2, a.n, pat, m, pw0, a.carry ? min(lm2, rm2) : 0u, act2);
+    const CmpResult c1 = group_compare<G>(a.text, s1, a.n, pat, m, pw0, CARRY ? min(lm1, rm1) : 0u, act1);
+    const CmpResult c2 = group_compare<G>(a.text, s2, a.n, pat, m, pw0, CARRY ? min(lm2, rm2) : 0u, act2);
     if (act1) { if (c1.gt) { lo = mid1 + 1; lm1 = c1.cpl; } else { hi = mid1; rm1 = c1.cpl; } }
     if (act2) { if (!c2.lt) { lo2 = mid2 + 1; lm2 = c2.cpl; } else { hi2 = mid2; rm2 = c2.cpl; } }
   }
@@ -246,9 +248,14 @@ int lsm_device(const TextView &tv, const u8 *d_pats, const u64 *d_pat_off, u64 Q
   const int G = group_lanes(max_pat_len);
   const u64 warps = div_up(Q, 32 / G);
   const unsigned blocks = (unsigned)div_up(warps * 32, 256);
-  if (G == 8) k_lsm<8><<<blocks, 256, 0, st>>>(a);
-  else if (G == 16) k_lsm<16><<<blocks, 256, 0, st>>>(a);
-  else k_lsm<32><<<blocks, 256, 0, st>>>(a);
+  // G == 8 / 16 are only chosen when every needle fits one comparison step (32 / 64 bytes)
+  const bool carry = a.carry && (max_pat_len == 0 || max_pat_len > 128);
+  // (for k_lsm<8> the CARRY instantiation is used although it cannot skip anything: it measures 813 M instead of
+  // 750 M queries/s on 32-byte needles -- a scheduling accident of the compiler, same results)
+  if (G == 8) { if (a.carry) k_lsm<8, true><<<blocks, 256, 0, st>>>(a); else k_lsm<8, false><<<blocks, 256, 0, st>>>(a); }
+  else if (G == 16) k_lsm<16, false><<<blocks, 256, 0, st>>>(a);
+  else if (carry) k_lsm<32, true><<<blocks, 256, 0, st>>>(a);
+  else k_lsm<32, false><<<blocks, 256, 0, st>>>(a);
   GSA_TRY(cudaGetLastError());
   return GSA_OK;
 }
@@ -260,9 +267,11 @@ int search_all_device(const TextView &tv, const u8 *d_pats, const u64 *d_pat_off
   const int G = group_lanes(max_pat_len);
   const u64 warps = div_up(Q, 32 / G);
   const unsigned blocks = (unsigned)div_up(warps * 32, 256);
-  if (G == 8) k_search_all<8><<<blocks, 256, 0, st>>>(a);
-  else if (G == 16) k_search_all<16><<<blocks, 256, 0, st>>>(a);
-  else k_search_all<32><<<blocks, 256, 0, st>>>(a);
+  const bool carry = a.carry && (max_pat_len == 0 || max_pat_len > 128);
+  if (G == 8) k_search_all<8, false><<<blocks, 256, 0, st>>>(a);
+  else if (G == 16) k_search_all<16, false><<<blocks, 256, 0, st>>>(a);
+  else if (carry) k_search_all<32, true><<<blocks, 256, 0, st>>>(a);
+  else k_search_all<32, false><<<blocks, 256, 0, st>>>(a);
   GSA_TRY(cudaGetLastError());
   return GSA_OK;
 }
