@@ -1295,9 +1295,14 @@ constexpr int RB_THREADS = 512;
 constexpr int RB_IPT = 8;
 constexpr int RB_TILE = RB_THREADS * RB_IPT;
 constexpr int HIST_THREADS = 512;
-constexpr int GA_THREADS = 512;
-constexpr int GA_IPT = 8;
-constexpr int GA_BLOCKS_PER_SM = 2;
+#ifndef GSA_GA_THREADS
+#define GSA_GA_THREADS 512
+#define GSA_GA_IPT 8
+#define GSA_GA_BLOCKS 2
+#endif
+constexpr int GA_THREADS = GSA_GA_THREADS;
+constexpr int GA_IPT = GSA_GA_IPT;
+constexpr int GA_BLOCKS_PER_SM = GSA_GA_BLOCKS;
 
 struct Layout {
   u64 *packed; u64 packed_words;
