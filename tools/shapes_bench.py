@@ -20,6 +20,17 @@ def fib(n):
     return np.frombuffer(b[:n], np.uint8).copy()
 
 
+def zipf_words(n, rng, vocab=50_000):
+    """Text-like: words of 2-10 letters drawn from a Zipf-distributed vocabulary, single spaces."""
+    lens = rng.integers(2, 11, vocab)
+    words = [bytes(rng.integers(97, 123, int(l), dtype=np.uint8)) + b" " for l in lens]
+    ranks = np.minimum(rng.zipf(1.2, n // 4), vocab) - 1
+    out = b"".join(words[r] for r in ranks)
+    while len(out) < n:
+        out += out
+    return np.frombuffer(out[:n], np.uint8).copy()
+
+
 def main():
     mib = int(sys.argv[1]) if len(sys.argv) > 1 else 256
     n = mib << 20
@@ -33,6 +44,8 @@ def main():
         "rep_period100k_rare": lambda: synth.repetitive(n, 6, period=100_000, mutation_rate=1e-5),
         "square": lambda: np.tile(rng.integers(0, 256, n // 4, dtype=np.uint8), 4),
         "binary_random": lambda: rng.integers(0, 2, n, dtype=np.uint8),
+        "zipf_words": lambda: zipf_words(n, rng),
+        "dna_with_repeats": lambda: np.concatenate([synth.acgt(n // 2, 7), synth.acgt(n // 2, 7)[::-1].copy()[: n // 4], synth.acgt(n // 4, 8)]),
         "text_like": lambda: (rng.integers(0, 27, n, dtype=np.uint8) + 97).astype(np.uint8),
         "run_in_random": lambda: np.concatenate([rng.integers(0, 256, n // 4, dtype=np.uint8), np.full(n // 2, 65, np.uint8),
                                                  rng.integers(0, 256, n // 4, dtype=np.uint8)]),
