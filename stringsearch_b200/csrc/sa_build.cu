@@ -24,7 +24,8 @@
 //   packed  u64[n*b/64 + 2]   keys u64[n] x2   vals(suffix) u32[n] x2
 //   pos u32[n] x2 (SA slot of each live element, SA order)
 //   lst u32[n] x2 (live suffixes, text order)   rank u32[n]   SA i32[n] (caller's)
-//   + histograms, pass / rebuild look-back descriptors, per-tile tail summaries.
+//   bag_sufx / bag_pos u32[n] x2 (members of tiny groups)   G u64[n] + tables per n/256 labels (huge groups)
+//   + histograms, pass look-back status, per-tile head / tail carries of the rebuild and slot kernels.
 #include "builder.h"
 #include <stdlib.h>
 
@@ -797,10 +798,9 @@ __global__ void __launch_bounds__(256) k_apply_g(const u32 *__restrict__ gupd, c
 //   old label in range -> nothing to write (the group keeps its label)
 //   otherwise          -> rank[suffix] = middle of the range + 1
 // and the slots of the non-unique elements are compacted for the next round.
-// The forward prefix (head, survivors, groups) travels through a decoupled look-back over
-// 16-byte tile descriptors; the backward one cannot wait on later tiles, so a first light
-// kernel records every tile's first tail slot and a one-block suffix-min scan turns that
-// into "first tail slot after tile t".
+// Neither scan waits on another block: a first light kernel (k_tail_summary) records every
+// tile's last head slot and first tail slot, and a one-block scan (k_tail_scan) turns them into
+// "last head slot before tile t" and "first tail slot after tile t".
 // ------------------------------------------------------------------------------------
 struct RebuildArgs {
   const u64 *keys;
@@ -982,8 +982,6 @@ __global__ void __launch_bounds__(THREADS, 2) k_rebuild(const RebuildArgs a) {
   constexpr int TILE = THREADS * IPT;
   __shared__ u32 s_wh[WARPS], s_wt[WARPS];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  // Tiles are taken in blockIdx order: the look-back only ever waits on lower-numbered
-  // blocks, which the hardware dispatches first.
   const u32 tile = blockIdx.x;
   const u32 L = a.L;
   const u32 l0 = tile * (u32)TILE + (u32)tid * IPT;

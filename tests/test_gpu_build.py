@@ -57,7 +57,7 @@ def test_every_length_up_to_80(port):
     ("two_symbols_nul_1M", lambda s: (s.random_bytes(1 << 20, 9) & 1).astype(np.uint8)),
     ("five_symbols_1M", lambda s: (s.random_bytes(1 << 20, 10) % 5).astype(np.uint8)),
     ("text_like_2M", lambda s: (s.random_bytes(2 << 20, 11) % 27 + 97).astype(np.uint8)),
-    # huge groups (>= 65536 suffixes sharing a prefix): the inert-majority path of the doubling rounds
+    # very large groups (>= 65536 suffixes sharing a prefix): the inert-majority path of the doubling rounds
     ("rep7_4M", lambda s: s.repetitive(4 << 20, 5, period=7, mutation_rate=1e-4)),
     ("rep40_6M_rare", lambda s: s.repetitive(6 << 20, 6, period=40, mutation_rate=3e-6)),
     ("run_in_random_4M", lambda s: np.concatenate([s.random_bytes(1 << 20, 12), np.full(2 << 20, 65, np.uint8), s.random_bytes(1 << 20, 13)])),
@@ -116,8 +116,8 @@ def test_sparse_mode_on_and_off(port, monkeypatch):
 
 
 def test_fuzz_repetitive_structures(ref):
-    """Randomised periodic / run-heavy / copy-heavy texts around the huge-group threshold (65 536
-    suffixes per group): every combination of verdicts (label moved, group became small, unique,
+    """Randomised periodic / run-heavy / copy-heavy texts with groups from a few hundred to a few hundred thousand suffixes
+    (the group tables start at 512): every combination of verdicts (label moved, group became small, unique,
     vanished), several huge groups interacting, NUL-heavy alphabets."""
     from stringsearch_b200 import _native as N
 
