@@ -160,6 +160,22 @@ def test_fuzz_repetitive_structures(ref):
         _assert_same(got, ref.sa_build(x), f"fuzz case {case} kind {kind} n={n}")
 
 
+@pytest.mark.parametrize("repeats", [31, 32, 33, 34, 255, 256, 257, 510, 511, 512, 513, 514, 1023, 1024, 1025, 3000])
+def test_group_sizes_around_the_class_thresholds(ref, repeats):
+    """A random block repeated r times (plus a few mutations) gives groups of about r suffixes:
+    r around 32 (bag / sort path), 256 (label granularity of the group tables) and 512 (group
+    tables), where groups change class while they shrink."""
+    rng = np.random.default_rng(repeats)
+    block = rng.integers(0, 4, 700, dtype=np.uint8)
+    t = np.tile(block, repeats)
+    for frac in (0.0, 3e-4):
+        x = t.copy()
+        k = int(x.size * frac)
+        if k:
+            x[rng.integers(0, x.size, k)] = rng.integers(0, 4, k)
+        _assert_same(_sort(x), ref.sa_build(x), f"repeats={repeats} mutations={k}")
+
+
 def test_inert_filter_on_and_off(ref, monkeypatch):
     """GSA_NO_INERT=1 sorts every live suffix in every round (no huge-group filter): same SA."""
     from stringsearch_b200 import synth
