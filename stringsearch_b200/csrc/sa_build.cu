@@ -1731,7 +1731,9 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
     u32 hc = 0;
     GSA_TRY(cudaMemcpyAsync(&hc, y.hcount + hcur, sizeof(u32), cudaMemcpyDeviceToHost, st));
     GSA_TRY(cudaStreamSynchronize(st));
-    if (hc > y.hcap / 2) { set_error("huge-group list overflow", __FILE__, __LINE__); return GSA_ECUDA; }
+    // at most n / HUGE_T groups survive k_huge_prepare (duplicates dropped) and at most as many are appended by a
+    // rebuild, so the list cannot outgrow its 2 n / HUGE_T + 4096 entries; anything else is a bug, not an input
+    if (hc >= y.hcap) { set_error("huge-group list overflow", __FILE__, __LINE__); return GSA_ECUDA; }
     GSA_TRY(cudaMemsetAsync(y.hcount + (hcur ^ 1), 0, sizeof(u32), st));
     GSA_TRY(cudaMemsetAsync(y.hcount + 2, 0, sizeof(u32), st));
     if (hc) {

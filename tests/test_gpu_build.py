@@ -192,6 +192,16 @@ def test_inert_filter_on_and_off(ref, monkeypatch):
     on = sum(r["sorted"] for r in st_on.rounds_list()[1:])
     off = sum(r["sorted"] for r in st_off.rounds_list()[1:])
     assert on < off // 2, (on, off)  # the filter really skipped most of the sorting work
+    # thousands of groups just above the group-table threshold, all of them re-created in every
+    # round when the filter is off (the list of huge groups then holds every label twice)
+    rng = np.random.default_rng(5)
+    t2 = np.tile(rng.integers(0, 256, 3000, dtype=np.uint8), 700)
+    t2[rng.integers(0, t2.size, 50)] ^= 1
+    exp2 = ref.sa_build(t2)
+    _assert_same(_sort(t2), exp2, "many groups, filter on")
+    monkeypatch.setenv("GSA_NO_INERT", "1")
+    _assert_same(_sort(t2), exp2, "many groups, filter off")
+    monkeypatch.delenv("GSA_NO_INERT", raising=False)
 
 
 def test_bwt_matches_reference(ref, sa_golden):
