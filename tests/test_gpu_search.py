@@ -210,3 +210,47 @@ def test_multi_device_partitions(port):
     s, l = part.longest_substring_match_batch(pats)
     es, el = port.part_lsm_batch(t, ps, sas, pats)
     assert (s == es).all() and (l == el).all()
+
+
+def test_full_size_part_4G_properties():
+    """BASELINE config 4 at full size: 2^32 bytes of ACGT in 8 partitions of 536 870 913 bytes
+    (sacapart lib.rs:43), all eight shards resident on one GPU.  Checked through properties:
+    the chunk plan, an O(n) sufcheck of every shard, and needles cut from the text -- inside a
+    partition (must be found in full), across a partition boundary (the match must be real and at
+    least as long as the part in front of the boundary; when that part is long enough to be unique
+    the match touches the end of the shard and must have been extended over it, lib.rs:77-84)."""
+    import ctypes as C
+
+    import torch
+
+    from stringsearch_b200 import _native as N, sacapart, synth
+
+    free, _ = torch.cuda.mem_get_info(0)
+    if free < 80 << 30:
+        pytest.skip(f"needs 80 GiB of free device memory, have {free >> 30}")
+    n, P, m = 1 << 32, 8, 48
+    t = synth.acgt(n, 4)
+    psa = sacapart.PartitionedSuffixArray(t, P, devices=[0])
+    ps = psa.partition_size()
+    assert psa.num_partitions() == 8 and ps == 536870913
+    for i in range(P):
+        ix = N.lib.gsa_part_shard(psa._h, i)
+        assert N.lib.gsa_index_len(ix) == min(ps, n - i * ps)
+        bad = C.c_int64(-1)
+        assert N.lib.gsa_index_verify(ix, C.byref(bad)) == 0, (i, bad.value)
+    rng = np.random.default_rng(9)
+    inside = [int(i * ps + o) for i in range(P) for o in rng.integers(0, ps - 2 * m, 40)]
+    across = [int(i * ps - k) for i in range(1, P) for k in rng.integers(1, m, 20)]  # starts k bytes before a boundary
+    needles = [t[o:o + m].tobytes() for o in inside + across]
+    start, length = psa.longest_substring_match_batch(needles)
+    for j, o in enumerate(inside + across):
+        s, l = int(start[j]), int(length[j])
+        assert t[s:s + l].tobytes() == needles[j][:l]
+        if j < len(inside):
+            assert l == m, (o, s, l)
+        else:
+            k = (-o) % ps  # bytes of the needle in front of the boundary
+            assert l >= k, (o, k, s, l)
+            if k >= 24:  # 4^24 >> n: no other place in the shard shares that many bytes
+                assert (s, l) == (o, m), (o, k, s, l)
+    psa.close()
