@@ -302,6 +302,14 @@ def run_ours(args, rank, local_rank, world):
     if args.e2e:
         e2e = run_e2e(args, N, torch, dist, dev, local_rank, world, t_host, d_sa, n, barrier)
 
+    # ---- queries at N > 1: the un-partitioned index replicated on every GPU, needles split across ranks ----
+    queries_multi = None
+    if args.queries and world > 1:
+        try:
+            queries_multi = bench_queries_replicated(dev, local_rank, rank, world, dist)
+        except Exception as e:  # secondary figure: never lose the headline line
+            queries_multi = {"error": repr(e)}
+
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -340,6 +348,8 @@ def run_ours(args, rank, local_rank, world):
                                          f"(oracle/_ref, gcc -O3 -DNDEBUG), 1 thread, {secs:.1f} s; host has {os.cpu_count()} cpus"}
     if lcp_info is not None:
         out["lcp"] = lcp_info
+    if queries_multi is not None:
+        out["queries"] = queries_multi
     if args.queries and world == 1:
         try:
             out["queries"] = bench_queries(dev, local_rank)
@@ -457,6 +467,59 @@ def bench_queries(dev, device_index):
         assert (cs == st[:qs]).all() and (cl == ln[:qs]).all(), "bench: GPU query results differ from the oracle"
         res["hit_fraction"] = float((ln == m).mean())
         return res
+    finally:
+        N.lib.gsa_index_destroy(h)
+
+
+def bench_queries_replicated(dev, device_index, rank, world, dist):
+    """BASELINE config 4 read literally ("1 GiB SA, N GPUs"): every rank builds the same 1 GiB ACGT
+    index, answers its 1/N of the 10M x 32 B needles, and the answers are all-gathered (NCCL)
+    inside the timed region.  queries/s = all needles / max over ranks of the device time."""
+    import torch
+    from stringsearch_b200 import _native as N
+    from stringsearch_b200 import synth
+
+    n, Q, m = 1 << 30, 10_000_000, 32
+    t = synth.acgt(n, 5)
+    h = C.c_void_p()
+    rc = N.lib.gsa_index_create(t.ctypes.data, n, device_index, C.byref(h), None)
+    if rc != 0:
+        raise RuntimeError(f"gsa_index_create rc={rc}: {N.last_error()}")
+    try:
+        flat, _ = synth.patterns_from_text(t, Q, m, 6)
+        per = (Q + world - 1) // world
+        lo, hi = min(Q, rank * per), min(Q, (rank + 1) * per)
+        d_p = torch.from_numpy(flat[lo * m:hi * m].copy()).to(dev)
+        d_o = (torch.arange(hi - lo + 1, dtype=torch.int64, device=dev) * m)
+        d_s = torch.zeros(per, dtype=torch.int64, device=dev)
+        d_l = torch.zeros(per, dtype=torch.int32, device=dev)
+        g_s = torch.empty(world * per, dtype=torch.int64, device=dev)
+        g_l = torch.empty(world * per, dtype=torch.int32, device=dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+
+        def step():
+            rc = N.lib.gsa_lsm_device(h, d_p.data_ptr(), d_o.data_ptr(), hi - lo, m, 0, 0, d_s.data_ptr(), d_l.data_ptr(), stream)
+            if rc != 0:
+                raise RuntimeError(f"gsa_lsm_device rc={rc}: {N.last_error()}")
+            dist.all_gather_into_tensor(g_s, d_s)
+            dist.all_gather_into_tensor(g_l, d_l)
+
+        step()
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            step()
+        e1.record()
+        dist.barrier()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1) / 3], dtype=torch.float64, device=dev)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return {"text": "1 GiB ACGT (seed 5), replicated on every GPU", "patterns": Q, "pattern_len": m, "gpus": world,
+                "longest_substring_match": {"queries_per_s": Q / (float(ms.item()) / 1e3), "ms": float(ms.item()),
+                                            "includes": "all-gather of (start, len) over NCCL"},
+                "hit_fraction": float((g_l[:Q] == m).double().mean().item())}
     finally:
         N.lib.gsa_index_destroy(h)
 

@@ -222,3 +222,102 @@ class DistributedPartitionedSuffixArray(StringIndex):
             self.close()
         except Exception:
             pass
+
+
+class ReplicatedSuffixArray(StringIndex):
+    """The un-partitioned index on every GPU, queries split across the ranks (SURVEY.md 8(e):
+    "1 GiB SA, 8 GPUs" -- pure data parallelism over the needles, answers identical to one GPU).
+
+    Every rank builds its own copy (the construction is deterministic, so the copies are equal
+    and no suffix array travels between GPUs); a query batch is broadcast from `src`, rank r
+    answers needles [r * ceil(Q / W), (r + 1) * ceil(Q / W)), and one all-gather per result
+    array puts the answers together on every rank."""
+
+    def __init__(self, text, device: int, group=None):
+        import torch.distributed as dist
+
+        self._dist = dist
+        self._group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self._text = N.as_u8(text)
+        self._device = device
+        self._h = self._build()
+
+    # device-touching steps (overridden with the oracle by the gloo CPU tests of the plumbing)
+    def _build(self):
+        h = C.c_void_p()
+        N.check(N.lib.gsa_index_create(N.ptr(self._text), self._text.size, self._device, C.byref(h), None), "gsa_index_create")
+        return h
+
+    def _answer_local(self, t_pat, t_off, q, t_start, t_len, dev, max_len: int = 0) -> None:
+        import torch
+
+        if not torch.cuda.is_available():
+            raise RuntimeError("stringsearch_b200 has no CPU path: the index needs a CUDA device")
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        rc = N.lib.gsa_lsm_device(self._h, t_pat.data_ptr(), t_off.data_ptr(), q, max_len, 0, 0,
+                                  t_start.data_ptr(), t_len.data_ptr(), stream)
+        N.check(rc, "gsa_lsm_device")
+
+    def _destroy(self, h) -> None:
+        N.lib.gsa_index_destroy(h)
+
+    def longest_substring_match_batch(self, needles, src: int = 0):
+        """Collective: every rank calls it; `needles` is only read on rank `src`.
+        Returns (start, len) numpy arrays for the whole batch on every rank."""
+        import torch
+
+        dist = self._dist
+        if self._text.size == 0:
+            raise IndexError("index out of bounds: the len is 0 but the index is 0")  # sacabase lib.rs:89-91
+        dev = torch.device("cuda", self._device) if torch.cuda.is_available() else torch.device("cpu")
+        if self.rank == src:
+            flat, off = N.pack_patterns(needles)
+            hdr = torch.tensor([off.size - 1, flat.size], dtype=torch.int64, device=dev)
+        else:
+            hdr = torch.zeros(2, dtype=torch.int64, device=dev)
+        if self.world > 1:
+            dist.broadcast(hdr, src=src, group=self._group)
+        q, nbytes = int(hdr[0]), int(hdr[1])
+        if self.rank == src:
+            t_off = torch.from_numpy(off.astype(np.int64)).to(dev)
+            t_pat = torch.from_numpy(flat if flat.size else np.zeros(1, np.uint8)).to(dev)
+        else:
+            t_off = torch.empty(q + 1, dtype=torch.int64, device=dev)
+            t_pat = torch.empty(max(1, nbytes), dtype=torch.uint8, device=dev)
+        if self.world > 1:
+            dist.broadcast(t_off, src=src, group=self._group)
+            dist.broadcast(t_pat, src=src, group=self._group)
+        # my slice of the batch: the offsets stay absolute, so the pattern buffer is shared as is
+        per = (q + self.world - 1) // self.world if q else 0
+        lo = min(q, self.rank * per)
+        hi = min(q, lo + per)
+        t_start = torch.zeros(max(per, 1), dtype=torch.int64, device=dev)
+        t_len = torch.zeros(max(per, 1), dtype=torch.int32, device=dev)
+        if hi > lo:
+            sub_off = t_off[lo:hi + 1].contiguous()
+            max_len = int((sub_off[1:] - sub_off[:-1]).max())
+            self._answer_local(t_pat, sub_off, hi - lo, t_start, t_len, dev, max_len)
+        if self.world > 1:
+            g_start = torch.empty(self.world * max(per, 1), dtype=torch.int64, device=dev)
+            g_len = torch.empty(self.world * max(per, 1), dtype=torch.int32, device=dev)
+            dist.all_gather_into_tensor(g_start, t_start, group=self._group)
+            dist.all_gather_into_tensor(g_len, t_len, group=self._group)
+            t_start, t_len = g_start, g_len
+        return t_start[:q].cpu().numpy().astype(np.uint64), t_len[:q].cpu().numpy().astype(np.uint32)
+
+    def longest_substring_match(self, needle) -> LongestCommonSubstring:
+        s, l = self.longest_substring_match_batch([needle])
+        return LongestCommonSubstring(self._text, int(s[0]), int(l[0]))
+
+    def close(self):
+        if self._h is not None:
+            self._destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -13,6 +13,38 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 
+def replicated(text, rank, world, local):
+    """ReplicatedSuffixArray: every rank holds the whole index and answers its slice of the batch."""
+    from stringsearch_b200 import sacapart
+
+    rsa = sacapart.ReplicatedSuffixArray(text, device=local)
+    rng = np.random.default_rng(6)
+    needles = None
+    if rank == 0:
+        needles = []
+        for i in range(5001):  # not a multiple of the world size
+            o = int(rng.integers(0, len(text) - 1))
+            b = bytearray(text[o:o + int(rng.integers(0, 300))].tobytes())
+            if b and i % 3 == 0:
+                b[-1] ^= 0x55
+            needles.append(bytes(b))
+    s, l = rsa.longest_substring_match_batch(needles)
+    ok = True
+    if rank == 0:
+        from oracle import oracle
+
+        port = oracle.port()
+        es, el = port.lsm_batch(text, port.sa_build(text), needles)
+        ok = bool((s == es).all() and (l == el).all())
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.broadcast(flag, src=0)
+    dist.barrier()
+    dist.destroy_process_group()
+    if rank == 0:
+        print("DIST_OK" if ok else "DIST_FAIL", flush=True)
+    sys.exit(0 if int(flag.item()) == 1 else 1)
+
+
 def main():
     from stringsearch_b200 import sacapart, synth
 
@@ -20,8 +52,10 @@ def main():
     local = int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    P = int(sys.argv[1]) if len(sys.argv) > 1 else 2 * world
     text = synth.repetitive(600_000, 31, period=700, mutation_rate=3e-3)  # same bytes on every rank
+    if len(sys.argv) > 1 and sys.argv[1] == "replicated":
+        return replicated(text, rank, world, local)
+    P = int(sys.argv[1]) if len(sys.argv) > 1 else 2 * world
     psa = sacapart.DistributedPartitionedSuffixArray(text, P, device=local)
     assert psa.local_partitions() == list(range(rank, psa.num_partitions(), world))
     rng = np.random.default_rng(5)

@@ -72,3 +72,61 @@ def test_distributed_query_plumbing_gloo(P, port):
         p.join(timeout=60)
     for rank, ok, got in res:
         assert ok, (rank, got, expect)
+
+
+def _worker_replicated(rank, world, port_no, text_bytes, needles, expect, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    from oracle import oracle
+    from stringsearch_b200.sacapart import ReplicatedSuffixArray
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port_no)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    port = oracle.port()
+    text = np.frombuffer(text_bytes, np.uint8)
+    answered = []
+
+    class OracleReplica(ReplicatedSuffixArray):
+        def _build(self):
+            return port.sa_build(self._text)
+
+        def _destroy(self, h):
+            pass
+
+        def _answer_local(self, t_pat, t_off, qn, t_start, t_len, dev, max_len=0):
+            pats, off = t_pat.numpy(), t_off.numpy()
+            answered.append(qn)
+            for j in range(qn):
+                s, l = port.longest_substring_match(self._text, self._h, pats[off[j]:off[j + 1]].tobytes())
+                t_start[j], t_len[j] = s, l
+
+    try:
+        rsa = OracleReplica(text, device=0)
+        s, l = rsa.longest_substring_match_batch(needles if rank == 0 else None)
+        got = list(zip(s.tolist(), l.tolist()))
+        q.put((rank, got == expect and sum(answered) <= (len(needles) + world - 1) // world, got))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("nq", [0, 1, 2, 5, 6])
+def test_replicated_query_plumbing_gloo(nq, port):
+    """ReplicatedSuffixArray: the batch is split across the ranks (each answers only its slice) and
+    the gathered answers are those of one un-partitioned index, in order."""
+    text = ("This is a rather long text. We can probably find matches that span two partitions. Oh yes. " * 2).encode()
+    needles = [b"rather long", b"text. We can", b"zzz", b"Oh yes. This", b"", b"We can probably"][:nq]
+    sa = port.sa_build(text)
+    expect = [tuple(port.longest_substring_match(text, sa, nd)) for nd in needles]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port_no = 31500 + (os.getpid() % 2000) + nq
+    procs = [ctx.Process(target=_worker_replicated, args=(r, 2, port_no, text, needles, expect, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, ok, got in res:
+        assert ok, (rank, got, expect)

@@ -28,6 +28,17 @@ def test_distributed_partitioned_query_nccl(P):
     assert r.returncode == 0 and "DIST_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
 
 
+def test_replicated_index_queries_nccl():
+    """ReplicatedSuffixArray over NCCL: needles split across the ranks, answers of one index."""
+    n = _ngpu()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={min(n, 4)}",
+           "--master-addr", "127.0.0.1", "--master-port", "29671", os.path.join(ROOT, "tests", "dist_worker.py"), "replicated"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "DIST_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
 def test_bench_two_ranks_small():
     """bench.py under torchrun on 2 GPUs (tiny workload): the JSON line carries the multi-GPU fields."""
     import json
