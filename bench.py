@@ -214,6 +214,8 @@ def run_ours(args, rank, local_rank, world):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # stdout carries exactly one JSON line: keep NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION) out of it
+        os.environ["NCCL_DEBUG"] = os.environ.get("GSA_NCCL_DEBUG", "WARN")
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
