@@ -215,7 +215,7 @@ def run_ours(args, rank, local_rank, world):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         # stdout carries exactly one JSON line: keep NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION) out of it
-        os.environ["NCCL_DEBUG"] = os.environ.get("GSA_NCCL_DEBUG", "WARN")
+        os.environ["NCCL_DEBUG"] = os.environ.get("GSA_NCCL_DEBUG", "NONE")  # (NCCL prints the banner at VERSION and at WARN)
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
