@@ -176,6 +176,32 @@ def test_group_sizes_around_the_class_thresholds(ref, repeats):
         _assert_same(_sort(x), ref.sa_build(x), f"repeats={repeats} mutations={k}")
 
 
+def test_fuzz_many_small_structured_texts(port):
+    """1500 small texts (1..20000 bytes) built from repeats of short blocks, runs, copies and
+    mutations over alphabets of 1..6 symbols: every one has many equal-prefix groups whose sizes
+    sit around the bag tile (480 + 32 entries), the warp and the 4096-element tiles."""
+    rng = np.random.default_rng(424242)
+    for case in range(1500):
+        n = int(rng.integers(1, 20000 if case % 10 == 0 else 3000))
+        sigma = int(rng.integers(1, 7))
+        kind = case % 5
+        if kind == 0:
+            t = np.tile(rng.integers(0, sigma, int(rng.integers(1, 40)), dtype=np.uint8), n)[:n]
+        elif kind == 1:
+            t = rng.integers(0, sigma, n, dtype=np.uint8)
+        elif kind == 2:  # copies of a block with single-symbol separators
+            b = rng.integers(0, sigma, int(rng.integers(1, 300)), dtype=np.uint8)
+            t = np.concatenate([np.concatenate([b, rng.integers(0, sigma, 1, dtype=np.uint8)]) for _ in range(n // (b.size + 1) + 1)])[:n]
+        elif kind == 3:  # runs
+            t = np.repeat(rng.integers(0, sigma, n // 7 + 1, dtype=np.uint8), rng.integers(1, 15, n // 7 + 1))[:n]
+        else:  # periodic with mutations
+            t = np.tile(rng.integers(0, sigma, int(rng.integers(2, 200)), dtype=np.uint8), n)[:n].copy()
+            k = max(1, n // 200)
+            t[rng.integers(0, n, k)] = rng.integers(0, sigma, k)
+        t = np.ascontiguousarray(t, dtype=np.uint8)
+        _assert_same(_sort(t), port.sa_build(t), f"case {case} kind {kind} n={t.size} sigma={sigma}")
+
+
 def test_inert_filter_on_and_off(ref, monkeypatch):
     """GSA_NO_INERT=1 sorts every live suffix in every round (no huge-group filter): same SA."""
     from stringsearch_b200 import synth
