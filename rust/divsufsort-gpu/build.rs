@@ -1,4 +1,4 @@
-// Counterpart of crates/cdivsufsort/build.rs:1-29: instead of four C files, compile the four
+// Counterpart of crates/cdivsufsort/build.rs:1-29: instead of four C files, compile the six
 // CUDA translation units of libgsa for sm_100a through the cc crate.
 fn main() {
     let csrc = "../../stringsearch_b200/csrc";
@@ -14,7 +14,7 @@ fn main() {
         .flag("-rdc=true")
         .include("../../include")
         .warnings(false);
-    for f in &["api.cu", "sa_build.cu", "search.cu", "verify.cu"] {
+    for f in &["api.cu", "sa_build.cu", "search.cu", "verify.cu", "bwt.cu", "lcp.cu"] {
         build.file(format!("{}/{}", csrc, f));
         println!("cargo:rerun-if-changed={}/{}", csrc, f);
     }
