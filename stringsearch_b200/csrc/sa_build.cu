@@ -551,10 +551,20 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_gather(const GatherArgs
     // every warp reserves its own output ranges: the lists stay in text order within a warp's
     // 32 * IPT candidates (which is what keeps the next round's reads coalesced), and no warp
     // ever waits for another one's loads at a barrier
+    // (both counters live in one 64-bit word -- live count low, sort count high -- so a warp needs one
+    // atomic, and none that returns a value when it has nothing to place: every warp of the grid
+    // hits this one address, 4 M times per round at 1 GiB)
     u32 bl = 0, bs = 0;
-    if (lane == 0) {
-      bl = wl ? atomicAdd(a.counter, wl) : 0u;
-      bs = ws ? atomicAdd(a.counter + 1, ws) : 0u;
+    if (lane == 0 && (wl | ws)) {
+      unsigned long long *both = reinterpret_cast<unsigned long long *>(a.counter);
+      const unsigned long long add = ((unsigned long long)ws << 32) | wl;
+      if (ws != 0u || a.lst_out != nullptr) {
+        const unsigned long long old = atomicAdd(both, add);
+        bl = (u32)old;
+        bs = (u32)(old >> 32);
+      } else {
+        atomicAdd(both, add);  // result unused: a reduction, nobody waits for it
+      }
     }
     bl = __shfl_sync(0xffffffffu, bl, 0);
     bs = __shfl_sync(0xffffffffu, bs, 0);
