@@ -1068,7 +1068,7 @@ __global__ void __launch_bounds__(THREADS, 2) k_rebuild(const RebuildArgs a) {
       tl[j] = cur;
     }
   }
-  // tiny groups headed here: one descriptor each, reserved with one atomic per warp
+  // tiny groups headed here: one descriptor each, reserved with one atomic per warp (per block: no faster)
   u32 dbase = 0;
   if (a.tiny_max) {
     u32 nd = 0, head = eh;
@@ -1144,10 +1144,12 @@ __global__ void __launch_bounds__(256) k_bag_append(const u64 *__restrict__ desc
                                                     u32 *__restrict__ bag_pos, u32 *__restrict__ bag_count) {
   // a warp expands 32 descriptors together: one reservation, then 32 entries per step, each lane
   // finding the descriptor of its entry by binary search over the warp's running sizes
+  __shared__ u32 s_tot[8];
+  __shared__ u32 s_base;
   const u32 q = blockIdx.x * blockDim.x + threadIdx.x;
-  const u32 lane = threadIdx.x & 31u;
+  const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const u32 nd = *desc_count;
-  if (q - lane >= nd) return;  // whole warp
+  if (blockIdx.x * blockDim.x >= nd) return;  // whole block
   const u64 d = (q < nd) ? desc[q] : 0ull;
   const u32 s = (u32)d, size = (u32)(d >> 32);
   u32 inc = size;
@@ -1157,9 +1159,18 @@ __global__ void __launch_bounds__(256) k_bag_append(const u64 *__restrict__ desc
     if ((int)lane >= o) inc += y;
   }
   const u32 total = __shfl_sync(0xffffffffu, inc, 31);
-  u32 base = 0;
-  if (lane == 0) base = atomicAdd(bag_count, total);
-  base = __shfl_sync(0xffffffffu, base, 0);
+  // one reservation per block (all blocks of the grid add to one counter)
+  if (lane == 0) s_tot[warp] = total;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    u32 t = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += s_tot[w];
+    s_base = t ? atomicAdd(bag_count, t) : 0u;
+  }
+  __syncthreads();
+  u32 base = s_base;
+  for (u32 w = 0; w < warp; ++w) base += s_tot[w];
   for (u32 e0 = 0; e0 < total; e0 += 32u) {
     const u32 e = e0 + lane;
     // first descriptor whose inclusive running size exceeds e
