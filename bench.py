@@ -499,29 +499,43 @@ def bench_queries_replicated(dev, device_index, rank, world, dist):
         g_l = torch.empty(world * per, dtype=torch.int32, device=dev)
         stream = torch.cuda.current_stream(dev).cuda_stream
 
-        def step():
+        d_left = torch.zeros(per, dtype=torch.int32, device=dev)
+        d_cnt = torch.zeros(per, dtype=torch.int32, device=dev)
+        g_left = torch.empty(world * per, dtype=torch.int32, device=dev)
+        g_cnt = torch.empty(world * per, dtype=torch.int32, device=dev)
+
+        def step_lsm():
             rc = N.lib.gsa_lsm_device(h, d_p.data_ptr(), d_o.data_ptr(), hi - lo, m, 0, 0, d_s.data_ptr(), d_l.data_ptr(), stream)
             if rc != 0:
                 raise RuntimeError(f"gsa_lsm_device rc={rc}: {N.last_error()}")
             dist.all_gather_into_tensor(g_s, d_s)
             dist.all_gather_into_tensor(g_l, d_l)
 
-        step()
-        dist.barrier()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(3):
+        def step_all():
+            rc = N.lib.gsa_search_all_device(h, d_p.data_ptr(), d_o.data_ptr(), hi - lo, m, d_left.data_ptr(), d_cnt.data_ptr(), stream)
+            if rc != 0:
+                raise RuntimeError(f"gsa_search_all_device rc={rc}: {N.last_error()}")
+            dist.all_gather_into_tensor(g_left, d_left)
+            dist.all_gather_into_tensor(g_cnt, d_cnt)
+
+        res = {"text": "1 GiB ACGT (seed 5), replicated on every GPU", "patterns": Q, "pattern_len": m, "gpus": world}
+        for name, step in (("longest_substring_match", step_lsm), ("search_all", step_all)):
             step()
-        e1.record()
-        dist.barrier()
-        torch.cuda.synchronize()
-        ms = torch.tensor([e0.elapsed_time(e1) / 3], dtype=torch.float64, device=dev)
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return {"text": "1 GiB ACGT (seed 5), replicated on every GPU", "patterns": Q, "pattern_len": m, "gpus": world,
-                "longest_substring_match": {"queries_per_s": Q / (float(ms.item()) / 1e3), "ms": float(ms.item()),
-                                            "includes": "all-gather of (start, len) over NCCL"},
-                "hit_fraction": float((g_l[:Q] == m).double().mean().item())}
+            dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(3):
+                step()
+            e1.record()
+            dist.barrier()
+            torch.cuda.synchronize()
+            ms = torch.tensor([e0.elapsed_time(e1) / 3], dtype=torch.float64, device=dev)
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            res[name] = {"queries_per_s": Q / (float(ms.item()) / 1e3), "ms": float(ms.item()),
+                         "includes": "all-gather of the two result arrays over NCCL"}
+        res["hit_fraction"] = float((g_l[:Q] == m).double().mean().item())
+        return res
     finally:
         N.lib.gsa_index_destroy(h)
 

@@ -263,14 +263,33 @@ class ReplicatedSuffixArray(StringIndex):
     def _destroy(self, h) -> None:
         N.lib.gsa_index_destroy(h)
 
+    def _answer_local_search_all(self, t_pat, t_off, q, t_left, t_count, dev, max_len: int = 0) -> None:
+        import torch
+
+        if not torch.cuda.is_available():
+            raise RuntimeError("stringsearch_b200 has no CPU path: the index needs a CUDA device")
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        rc = N.lib.gsa_search_all_device(self._h, t_pat.data_ptr(), t_off.data_ptr(), q, max_len,
+                                         t_left.data_ptr(), t_count.data_ptr(), stream)
+        N.check(rc, "gsa_search_all_device")
+
     def longest_substring_match_batch(self, needles, src: int = 0):
         """Collective: every rank calls it; `needles` is only read on rank `src`.
         Returns (start, len) numpy arrays for the whole batch on every rank."""
+        if self._text.size == 0:
+            raise IndexError("index out of bounds: the len is 0 but the index is 0")  # sacabase lib.rs:89-91
+        a, b = self._split_and_gather(needles, src, "lsm")
+        return a.astype(np.uint64), b.astype(np.uint32)
+
+    def search_all_batch(self, needles, src: int = 0):
+        """sa_search for every needle (utils.c:258-325): -> (left, count) int32 arrays, on every rank."""
+        a, b = self._split_and_gather(needles, src, "search_all")
+        return a.astype(np.int32), b.astype(np.int32)
+
+    def _split_and_gather(self, needles, src: int, what: str):
         import torch
 
         dist = self._dist
-        if self._text.size == 0:
-            raise IndexError("index out of bounds: the len is 0 but the index is 0")  # sacabase lib.rs:89-91
         dev = torch.device("cuda", self._device) if torch.cuda.is_available() else torch.device("cpu")
         if self.rank == src:
             flat, off = N.pack_patterns(needles)
@@ -293,19 +312,23 @@ class ReplicatedSuffixArray(StringIndex):
         per = (q + self.world - 1) // self.world if q else 0
         lo = min(q, self.rank * per)
         hi = min(q, lo + per)
-        t_start = torch.zeros(max(per, 1), dtype=torch.int64, device=dev)
+        first = torch.int64 if what == "lsm" else torch.int32
+        t_start = torch.zeros(max(per, 1), dtype=first, device=dev)
         t_len = torch.zeros(max(per, 1), dtype=torch.int32, device=dev)
         if hi > lo:
             sub_off = t_off[lo:hi + 1].contiguous()
             max_len = int((sub_off[1:] - sub_off[:-1]).max())
-            self._answer_local(t_pat, sub_off, hi - lo, t_start, t_len, dev, max_len)
+            if what == "lsm":
+                self._answer_local(t_pat, sub_off, hi - lo, t_start, t_len, dev, max_len)
+            else:
+                self._answer_local_search_all(t_pat, sub_off, hi - lo, t_start, t_len, dev, max_len)
         if self.world > 1:
-            g_start = torch.empty(self.world * max(per, 1), dtype=torch.int64, device=dev)
+            g_start = torch.empty(self.world * max(per, 1), dtype=first, device=dev)
             g_len = torch.empty(self.world * max(per, 1), dtype=torch.int32, device=dev)
             dist.all_gather_into_tensor(g_start, t_start, group=self._group)
             dist.all_gather_into_tensor(g_len, t_len, group=self._group)
             t_start, t_len = g_start, g_len
-        return t_start[:q].cpu().numpy().astype(np.uint64), t_len[:q].cpu().numpy().astype(np.uint32)
+        return t_start[:q].cpu().numpy(), t_len[:q].cpu().numpy()
 
     def longest_substring_match(self, needle) -> LongestCommonSubstring:
         s, l = self.longest_substring_match_batch([needle])

@@ -34,8 +34,13 @@ def replicated(text, rank, world, local):
         from oracle import oracle
 
         port = oracle.port()
-        es, el = port.lsm_batch(text, port.sa_build(text), needles)
+        sa = port.sa_build(text)
+        es, el = port.lsm_batch(text, sa, needles)
         ok = bool((s == es).all() and (l == el).all())
+    left, cnt = rsa.search_all_batch(needles)
+    if rank == 0:
+        eleft, ecnt = port.search_all_batch(text, sa, needles)
+        ok = ok and bool((left == eleft).all() and (cnt == ecnt).all())
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, src=0)
     dist.barrier()
