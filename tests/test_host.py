@@ -52,6 +52,21 @@ def test_argument_checks_without_gpu():
     assert L.gsa_part_create(N.ptr(t), 2, 0, None, 0, C.byref(h)) == N.GSA_EPANIC  # sacapart lib.rs:43
     assert L.gsa_build_workspace_bytes(0) == 0
     assert L.gsa_build_workspace_bytes(1 << 20) > 33 * (1 << 20)
+    # divbwt / inverse_bw_transform / lcp: the checks of divsufsort.c:377-381 and utils.c:120-124 come first
+    u = np.zeros(2, np.uint8)
+    assert L.gsa_divbwt(None, N.ptr(u), None, 2) == N.GSA_EINVAL and L.gsa_divbwt(N.ptr(t), N.ptr(u), None, -1) == N.GSA_EINVAL
+    assert L.gsa_divbwt(N.ptr(t), N.ptr(u), None, 0) == 0
+    assert L.gsa_divbwt(N.ptr(t), N.ptr(u), None, 1) == 1 and u[0] == t[0]
+    for n_, idx in ((-1, 0), (2, -1), (2, 3), (2, 0)):
+        assert L.gsa_inverse_bw_transform(N.ptr(t), N.ptr(u), None, n_, idx) == N.GSA_EINVAL
+    assert L.gsa_inverse_bw_transform(None, N.ptr(u), None, 2, 1) == N.GSA_EINVAL
+    assert L.gsa_inverse_bw_transform(N.ptr(t), N.ptr(u), None, 0, 0) == 0
+    assert L.gsa_inverse_bw_transform(N.ptr(t), N.ptr(u), None, 1, 1) == 0 and u[0] == t[0]
+    lcp = np.zeros(2, np.int32)
+    assert L.gsa_lcp(N.ptr(t), N.ptr(sa), N.ptr(lcp), -1, 0) == N.GSA_EINVAL
+    assert L.gsa_lcp(None, N.ptr(sa), N.ptr(lcp), 2, 0) == N.GSA_EINVAL and L.gsa_lcp(N.ptr(t), None, N.ptr(lcp), 2, 0) == N.GSA_EINVAL
+    assert L.gsa_lcp(N.ptr(t), N.ptr(sa), None, 2, 0) == N.GSA_EINVAL and L.gsa_lcp(N.ptr(t), N.ptr(sa), N.ptr(lcp), 0, 0) == 0
+    assert L.gsa_lcp_workspace_bytes(1 << 20) >= 4 * (1 << 20) and L.gsa_inverse_bwt_workspace_bytes(1 << 20) >= 12 * (1 << 20)
 
 
 def test_python_mirror_preconditions():
