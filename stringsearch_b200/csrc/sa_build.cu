@@ -1271,31 +1271,36 @@ __global__ void __launch_bounds__(BAG_THREADS) k_bag_refine(const BagArgs a) {
   const u32 bal = __ballot_sync(0xffffffffu, surv);
   if (lane == 0u) { s_warp[warp] = (u32)__popc(bal); s_bal[warp] = bal; }
   __syncthreads();
+  // The reservation of the block's output range is one atomic on a counter shared by the whole grid;
+  // everything that does not need its result is done while it is in flight.
   if (tid == 0u) {
     u32 tot = 0;
 #pragma unroll
     for (u32 w = 0; w < NW; ++w) tot += s_warp[w];
     s_base = tot ? atomicAdd(a.count_out, tot) : 0u;
   }
-  __syncthreads();
-  if (!mine) return;
   const u32 sufx = s_sfx[tid];
-  if (!surv) {
+  u32 o = 0;
+  if (mine && !surv) {
     a.SA[slot] = (i32)sufx;
     a.rank[sufx] = RANK_DEAD | (slot + 1u);
-    return;
+  } else if (surv) {
+    u32 in_group_before = 0;
+    for (u32 m = g0; m < g1; ++m) {
+      const u32 sm = s_slot[m];
+      in_group_before += ((sm & BAG_HEAD) && (sm & ~BAG_HEAD) < slot) ? 1u : 0u;
+    }
+    if (tiny_label(s1) != tiny_label(gs)) a.rank[sufx] = tiny_label(s1);
+    u32 before_group = (u32)__popc(s_bal[g0 >> 5] & ((1u << (g0 & 31u)) - 1u));  // survivors in front of my group's head
+    for (u32 w = 0; w < (g0 >> 5); ++w) before_group += s_warp[w];
+    o = before_group + in_group_before;
   }
-  u32 in_group_before = 0;
-  for (u32 m = g0; m < g1; ++m) {
-    const u32 sm = s_slot[m];
-    in_group_before += ((sm & BAG_HEAD) && (sm & ~BAG_HEAD) < slot) ? 1u : 0u;
+  __syncthreads();
+  if (surv) {
+    o += s_base;
+    a.sufx_out[o] = sufx;
+    a.pos_out[o] = slot | (slot == s1 ? BAG_HEAD : 0u);
   }
-  if (tiny_label(s1) != tiny_label(gs)) a.rank[sufx] = tiny_label(s1);
-  u32 before_group = (u32)__popc(s_bal[g0 >> 5] & ((1u << (g0 & 31u)) - 1u));  // survivors in front of my group's head
-  for (u32 w = 0; w < (g0 >> 5); ++w) before_group += s_warp[w];
-  const u32 o = s_base + before_group + in_group_before;
-  a.sufx_out[o] = sufx;
-  a.pos_out[o] = slot | (slot == s1 ? BAG_HEAD : 0u);
 }
 
 // ------------------------------------------------------------------------------------
