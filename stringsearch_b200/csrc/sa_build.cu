@@ -1136,7 +1136,7 @@ __global__ void __launch_bounds__(THREADS, 2) k_rebuild(const RebuildArgs a) {
 //   k_bag_gather   r2 = label(suffix + h) for every entry (the one random read of the round)
 //   k_bag_refine   one thread per entry, one block per 960 entries (+ 64 of overlap, so that a
 //                  group never straddles a block): order the members of each group by r2 (rank
-//                  by counting, groups have <= 64 members), split into runs of equal r2,
+//                  by counting, groups have <= TINY_MAX members), split into runs of equal r2,
 //                  finalise the unique ones, re-label and re-append the others.
 // ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_bag_append(const u64 *__restrict__ desc, const u32 *__restrict__ desc_count,
