@@ -1134,8 +1134,8 @@ __global__ void __launch_bounds__(THREADS, 2) k_rebuild(const RebuildArgs a) {
 // The bag (see pick_label): tiny groups, refined without the radix sort.
 //   k_bag_append   descriptors written by a rebuild -> flattened (suffix, slot | HEAD) entries
 //   k_bag_gather   r2 = label(suffix + h) for every entry (the one random read of the round)
-//   k_bag_refine   one thread per entry, one block per 960 entries (+ 64 of overlap, so that a
-//                  group never straddles a block): order the members of each group by r2 (rank
+//   k_bag_refine   one thread per entry, one block per BAG_TILE entries (+ TINY_MAX of overlap, so
+//                  that a group never straddles a block): order the members of each group by r2 (rank
 //                  by counting, groups have <= TINY_MAX members), split into runs of equal r2,
 //                  finalise the unique ones, re-label and re-append the others.
 // ------------------------------------------------------------------------------------
