@@ -116,11 +116,19 @@ static void parallel_memcpy(char *dst, const char *src, size_t bytes) {
   const size_t per = align_up(div_up(bytes, kStageThreads), 4096);
   std::thread th[kStageThreads - 1];
   int started = 0;
+  size_t done_to = std::min(bytes, per);  // [0, done_to) is copied by this thread
   for (int t = 1; t < kStageThreads; ++t) {
     const size_t lo = std::min(bytes, per * (size_t)t), hi = std::min(bytes, lo + per);
-    if (hi > lo) th[started++] = std::thread([=] { memcpy(dst + lo, src + lo, hi - lo); });
+    if (hi <= lo) break;
+    try {
+      th[started] = std::thread([=] { memcpy(dst + lo, src + lo, hi - lo); });
+      ++started;
+    } catch (...) {  // no thread to be had: this one copies the rest as well (nothing may escape the C ABI)
+      memcpy(dst + lo, src + lo, bytes - lo);
+      break;
+    }
   }
-  memcpy(dst, src, std::min(bytes, per));
+  memcpy(dst, src, done_to);
   for (int t = 0; t < started; ++t) th[t].join();
 }
 
