@@ -6,6 +6,7 @@
 // no usable GPU every compute entry point returns GSA_ECUDA.
 #include <algorithm>
 #include <mutex>
+#include <new>
 #include <string>
 #include <thread>
 #include <vector>
@@ -687,12 +688,18 @@ int32_t gsa_search_all_batch(const gsa_index *ix, const uint8_t *pats, const uin
 }
 
 int32_t gsa_contains_batch(const gsa_index *ix, const uint8_t *pats, const uint64_t *pat_off, uint64_t Q,
-                           uint8_t *out) {
+                           uint8_t *out) try {
   if (Q > 0 && !out) return GSA_EINVAL;
   std::vector<i32> left((size_t)Q), count((size_t)Q);
   GSA_TRY_RC(gsa_search_all_batch(ix, pats, pat_off, Q, left.data(), count.data()));
   for (u64 q = 0; q < Q; ++q) out[q] = count[q] > 0;
   return GSA_OK;
+} catch (const std::bad_alloc &) {  // nothing may escape the C ABI
+  gsa::set_error("out of host memory", __FILE__, __LINE__);
+  return GSA_ENOMEM;
+} catch (...) {
+  gsa::set_error("unexpected C++ exception", __FILE__, __LINE__);
+  return GSA_ECUDA;
 }
 
 int32_t gsa_lsm_device(const gsa_index *ix, const uint8_t *d_pats, const uint64_t *d_pat_off, uint64_t Q,
@@ -722,7 +729,7 @@ int32_t gsa_lsm_reduce_device(uint64_t *d_start, uint32_t *d_len, uint64_t Q, ui
 static const u64 kDefaultHalo = 4096;
 
 int32_t gsa_part_create(const uint8_t *T, uint64_t n, uint64_t num_partitions, const int32_t *devices, int32_t ndev,
-                        gsa_part **out) {
+                        gsa_part **out) try {
   if (!out) return GSA_EINVAL;
   *out = nullptr;
   if (T == nullptr && n > 0) return GSA_EINVAL;
@@ -768,6 +775,12 @@ int32_t gsa_part_create(const uint8_t *T, uint64_t n, uint64_t num_partitions, c
     }
   *out = p;
   return GSA_OK;
+} catch (const std::bad_alloc &) {  // nothing may escape the C ABI
+  gsa::set_error("out of host memory", __FILE__, __LINE__);
+  return GSA_ENOMEM;
+} catch (...) {
+  gsa::set_error("unexpected C++ exception", __FILE__, __LINE__);
+  return GSA_ECUDA;
 }
 
 uint64_t gsa_part_num_partitions(const gsa_part *p) { return p ? p->shards.size() : 0; }
@@ -783,7 +796,7 @@ void gsa_part_destroy(gsa_part *p) {
 }
 
 int32_t gsa_part_lsm_batch(gsa_part *p, const uint8_t *pats, const uint64_t *pat_off, uint64_t Q, uint64_t *out_start,
-                           uint32_t *out_len) {
+                           uint32_t *out_len) try {
   if (!p || (Q > 0 && (!out_start || !out_len))) return GSA_EINVAL;
   GSA_TRY_RC(check_patterns(pats, pat_off, Q));
   if (p->shards.empty()) {  // lib.rs:94-96: expect() on None
@@ -844,6 +857,12 @@ int32_t gsa_part_lsm_batch(gsa_part *p, const uint8_t *pats, const uint64_t *pat
   GSA_TRY(cudaMemcpyAsync(out_len, dev[0].len.p, (size_t)Q * 4, cudaMemcpyDeviceToHost, dev[0].st.s));
   GSA_TRY(cudaStreamSynchronize(dev[0].st.s));
   return GSA_OK;
+} catch (const std::bad_alloc &) {  // nothing may escape the C ABI
+  gsa::set_error("out of host memory", __FILE__, __LINE__);
+  return GSA_ENOMEM;
+} catch (...) {
+  gsa::set_error("unexpected C++ exception", __FILE__, __LINE__);
+  return GSA_ECUDA;
 }
 
 }  // extern "C"
