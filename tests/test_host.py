@@ -175,3 +175,12 @@ def test_synth_shapes():
     assert x.size == 10_000 and (x[:100] != x[100:200]).sum() < 20
     flat, off = synth.patterns_from_text(synth.acgt(5000, 5), 10, 32, 6)
     assert flat.size == 320 and off.tolist() == list(range(0, 321, 32))
+
+
+def test_tools_and_entry_points_compile():
+    """bench.py, __graft_entry__.py and every script under tools/ at least parse (they only run on a GPU box)."""
+    import glob
+    import py_compile
+
+    for f in [os.path.join(ROOT, "bench.py"), os.path.join(ROOT, "__graft_entry__.py")] + sorted(glob.glob(os.path.join(ROOT, "tools", "*.py"))):
+        py_compile.compile(f, doraise=True)
