@@ -184,3 +184,14 @@ def test_tools_and_entry_points_compile():
 
     for f in [os.path.join(ROOT, "bench.py"), os.path.join(ROOT, "__graft_entry__.py")] + sorted(glob.glob(os.path.join(ROOT, "tools", "*.py"))):
         py_compile.compile(f, doraise=True)
+
+
+def test_header_is_plain_c99(tmp_path):
+    """include/gsa.h is the drop-in boundary: it must be includable from C (plain pointers and sizes only)."""
+    import subprocess
+
+    src = tmp_path / "t.c"
+    src.write_text('#include "gsa.h"\nint main(void) { return (int)gsa_build_workspace_bytes(0); }\n')
+    r = subprocess.run(["/usr/bin/gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                        "-fsyntax-only", str(src)], capture_output=True, text=True)
+    assert r.returncode == 0 and not r.stderr.strip(), r.stderr
