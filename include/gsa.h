@@ -151,7 +151,11 @@ int32_t gsa_sufcheck(const uint8_t *T, const int32_t *SA, int32_t n, int32_t dev
  * -------------------------------------------------------------------------- */
 typedef struct gsa_index gsa_index;
 int32_t gsa_index_create(const uint8_t *T, int64_t n, int32_t device, gsa_index **out, gsa_build_stats *stats);
-int32_t gsa_index_from_parts(const uint8_t *T, const int32_t *SA, int64_t n, int32_t device, gsa_index **out);
+/* sa_len must equal n (GSA_EINVAL otherwise: the handle keeps one length for both arrays), and every
+ * entry of SA must be a text position (checked on the device; GSA_EPANIC otherwise -- the reference
+ * panics on its slice bounds check the first time such an entry is used, lib.rs:53-57). */
+int32_t gsa_index_from_parts(const uint8_t *T, int64_t n, const int32_t *SA, int64_t sa_len, int32_t device,
+                             gsa_index **out);
 int64_t gsa_index_len(const gsa_index *ix);
 int32_t gsa_index_device(const gsa_index *ix);
 int32_t gsa_index_sa(const gsa_index *ix, int32_t *out_sa /* host, n entries */);
@@ -218,6 +222,8 @@ int32_t gsa_lsm_reduce_device(uint64_t *d_start, uint32_t *d_len, uint64_t Q, ui
  * `T` (host) must stay valid for the lifetime of the handle, as the reference's
  * borrow `&'a [u8]` requires (:31); it is used to top up the per-shard halo that the
  * may_extend rule (:77-84) reads past the shard end.
+ * Queries on one handle are serialised internally (a query may grow a shard's halo, which replaces
+ * its device text buffer); different handles are independent.
  * num_partitions == 0 -> GSA_EPANIC (the reference divides by zero, :43);
  * querying a handle with zero partitions (empty text) -> GSA_EPANIC (:94-96).
  * -------------------------------------------------------------------------- */
@@ -254,6 +260,8 @@ const char *gsa_last_error(void);
 const char *gsa_version(void);
 /* Number of visible CUDA devices (<= 0: no usable GPU). */
 int32_t gsa_device_count(void);
+/* The calling thread's current CUDA device (what gsa_divsufsort() builds on); 0 if there is none. */
+int32_t gsa_current_device(void);
 
 #ifdef __cplusplus
 }

@@ -19,7 +19,7 @@ pub struct GsaPart {
 
 extern "C" {
     fn gsa_divsufsort(T: *const u8, SA: *mut i32, n: i32) -> i32;
-    fn gsa_index_from_parts(T: *const u8, SA: *const i32, n: i64, device: i32, out: *mut *mut GsaIndex) -> i32;
+    fn gsa_index_from_parts(T: *const u8, n: i64, SA: *const i32, sa_len: i64, device: i32, out: *mut *mut GsaIndex) -> i32;
     fn gsa_index_verify(ix: *const GsaIndex, bad_index: *mut i64) -> i32;
     fn gsa_index_destroy(ix: *mut GsaIndex);
     fn gsa_lsm_batch(ix: *const GsaIndex, pats: *const u8, pat_off: *const u64, q: u64, out_start: *mut u64, out_len: *mut u32) -> i32;
@@ -97,8 +97,10 @@ pub struct GpuSuffixArray<'a> {
 
 impl<'a> GpuSuffixArray<'a> {
     pub fn new(text: &'a [u8], sa: Vec<i32>, device: i32) -> Self {
+        assert_eq!(text.len(), sa.len(), "text and suffix array should have same len");
         let mut ix = std::ptr::null_mut();
-        let rc = unsafe { gsa_index_from_parts(text.as_ptr(), sa.as_ptr(), text.len() as i64, device, &mut ix) };
+        // the library re-checks the length and range-checks every entry on the device (GSA_EPANIC)
+        let rc = unsafe { gsa_index_from_parts(text.as_ptr(), text.len() as i64, sa.as_ptr(), sa.len() as i64, device, &mut ix) };
         assert_eq!(0, rc, "{}", last_error());
         Self { text, sa, ix }
     }

@@ -108,7 +108,7 @@ def _load() -> C.CDLL:
         "gsa_sufcheck_device": ([vp, vp, C.c_int32, vp, i64p], C.c_int32),
         "gsa_sufcheck": ([vp, vp, C.c_int32, C.c_int32, i64p], C.c_int32),
         "gsa_index_create": ([vp, C.c_int64, C.c_int32, C.POINTER(vp), C.POINTER(BuildStats)], C.c_int32),
-        "gsa_index_from_parts": ([vp, vp, C.c_int64, C.c_int32, C.POINTER(vp)], C.c_int32),
+        "gsa_index_from_parts": ([vp, C.c_int64, vp, C.c_int64, C.c_int32, C.POINTER(vp)], C.c_int32),
         "gsa_index_create_shard": ([vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int32, C.POINTER(vp), C.POINTER(BuildStats)], C.c_int32),
         "gsa_index_len": ([vp], C.c_int64),
         "gsa_index_device": ([vp], C.c_int32),
@@ -135,6 +135,7 @@ def _load() -> C.CDLL:
         "gsa_last_error": ([], C.c_char_p),
         "gsa_version": ([], C.c_char_p),
         "gsa_device_count": ([], C.c_int32),
+        "gsa_current_device": ([], C.c_int32),
     }
     for name, (args, res) in sig.items():
         fn = getattr(L, name)  # AttributeError here = header / library mismatch: fail loudly
@@ -151,6 +152,11 @@ EXPORTED_SYMBOLS = lib._gsa_symbols
 def last_error() -> str:
     s = lib.gsa_last_error()
     return s.decode(errors="replace") if s else ""
+
+
+def current_device() -> int:
+    """The calling thread's current CUDA device (the one gsa_divsufsort() builds on)."""
+    return int(lib.gsa_current_device())
 
 
 def check(rc: int, where: str) -> None:
@@ -176,6 +182,13 @@ def pack_patterns(pats):
     if isinstance(pats, tuple) and len(pats) == 2:
         flat = np.ascontiguousarray(pats[0], dtype=np.uint8)
         off = np.ascontiguousarray(pats[1], dtype=np.uint64)
+        # the library reads flat[off[q] : off[q+1]] for every q: refuse offsets that leave the buffer
+        if off.ndim != 1 or off.size < 1:
+            raise ValueError("pattern offsets must be a 1-d array of Q + 1 entries")
+        if off.size > 1 and bool((off[1:] < off[:-1]).any()):
+            raise ValueError("pattern offsets must be non-decreasing")
+        if int(off[-1]) > flat.size:
+            raise ValueError(f"pattern offsets end at {int(off[-1])} but only {flat.size} pattern bytes were given")
         return flat, off
     lens = np.fromiter((len(p) for p in pats), dtype=np.uint64, count=len(pats))
     off = np.zeros(len(pats) + 1, dtype=np.uint64)

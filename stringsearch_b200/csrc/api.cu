@@ -5,6 +5,7 @@
 // All compute is in sa_build.cu / search.cu / verify.cu.  There is no CPU fallback: with
 // no usable GPU every compute entry point returns GSA_ECUDA.
 #include <algorithm>
+#include <memory>
 #include <mutex>
 #include <new>
 #include <string>
@@ -270,6 +271,7 @@ struct gsa_part {
   u64 partition_size = 0;
   std::vector<gsa_index *> shards;
   std::vector<int> devices;
+  std::mutex query_mu;  // gsa_part_lsm_batch may re-allocate a shard's text (halo top-up): one query at a time
 };
 
 extern "C" {
@@ -282,6 +284,8 @@ int32_t gsa_device_count(void) {
   if (cudaGetDeviceCount(&c) != cudaSuccess) { cudaGetLastError(); return 0; }
   return c;
 }
+
+int32_t gsa_current_device(void) { return current_device(); }
 
 void gsa_release_cached_memory(void) {
   std::lock_guard<std::mutex> lk(g_scratch.mu);
@@ -529,7 +533,16 @@ static int index_create_impl(const u8 *T_full, u64 n_full, u64 offset, u64 len, 
     if (len + halo > 0) GSA_TRY(cudaMemcpyAsync(d_T.p, T_full + offset, (size_t)(len + halo), cudaMemcpyHostToDevice, st.s));
     if (host_sa) {
       if (len > 0) GSA_TRY(cudaMemcpyAsync(d_SA.p, host_sa, (size_t)len * 4, cudaMemcpyHostToDevice, st.s));
-      GSA_TRY(cudaStreamSynchronize(st.s));
+      // a caller-supplied SA: every entry must be a text position, or the search kernels would read
+      // outside the text (the reference panics on its slice bounds check instead)
+      i64 bad = -1;
+      GSA_TRY_RC(sa_range_check_device(d_SA.p, (u32)len, st.s, &bad));
+      if (bad >= 0) {
+        char msg[128];
+        snprintf(msg, sizeof msg, "suffix array entry %lld is out of range for a text of %llu bytes", (long long)bad, (unsigned long long)len);
+        set_error(msg, __FILE__, __LINE__);
+        return GSA_EPANIC;
+      }
       return GSA_OK;
     }
     return build_sa_device(d_T.p, d_SA.p, (u32)len, nullptr, 0, st.s, stats);
@@ -547,8 +560,13 @@ int32_t gsa_index_create(const uint8_t *T, int64_t n, int32_t device, gsa_index 
   return index_create_impl(T, (u64)n, 0, (u64)n, 0, device, false, nullptr, out, stats);
 }
 
-int32_t gsa_index_from_parts(const uint8_t *T, const int32_t *SA, int64_t n, int32_t device, gsa_index **out) {
+int32_t gsa_index_from_parts(const uint8_t *T, int64_t n, const int32_t *SA, int64_t sa_len, int32_t device,
+                             gsa_index **out) {
   if (n < 0 || (n > 0 && SA == nullptr)) return GSA_EINVAL;
+  if (sa_len != n) {
+    set_error("text and suffix array should have same len", __FILE__, __LINE__);
+    return GSA_EINVAL;
+  }
   static const i32 dummy = 0;
   return index_create_impl(T, (u64)n, 0, (u64)n, 0, device, false, n > 0 ? SA : &dummy, out, nullptr);
 }
@@ -737,7 +755,9 @@ int32_t gsa_part_create(const uint8_t *T, uint64_t n, uint64_t num_partitions, c
     set_error("attempt to divide by zero (num_partitions == 0)", __FILE__, __LINE__);
     return GSA_EPANIC;
   }
-  gsa_part *p = new (std::nothrow) gsa_part();
+  struct PartFree { void operator()(gsa_part *q) const { gsa_part_destroy(q); } };
+  std::unique_ptr<gsa_part, PartFree> owner(new (std::nothrow) gsa_part());  // freed with its shards on every error path
+  gsa_part *p = owner.get();
   if (!p) return GSA_ENOMEM;
   p->text = T;
   p->n = n;
@@ -762,18 +782,27 @@ int32_t gsa_part_create(const uint8_t *T, uint64_t n, uint64_t num_partitions, c
   if (nd == 1) {
     worker(0);
   } else {
-    std::vector<std::thread> th;
-    for (size_t k = 0; k < nd; ++k) th.emplace_back(worker, k);
-    for (auto &t : th) t.join();
+    // joins whatever was started, also when a later spawn throws (a joinable std::thread that is
+    // destroyed calls std::terminate before any handler of this function runs)
+    struct Joiner {
+      std::vector<std::thread> th;
+      ~Joiner() { for (auto &t : th) if (t.joinable()) t.join(); }
+    } j;
+    j.th.reserve(nd);
+    for (size_t k = 0; k < nd; ++k) {
+      try {
+        j.th.emplace_back(worker, k);
+      } catch (...) {  // no thread to be had: this one builds the device's shards itself
+        worker(k);
+      }
+    }
   }
   for (size_t k = 0; k < nd; ++k)
     if (rcs[k] != GSA_OK) {
       g_last_error = errs[k];
-      const int rc = rcs[k];
-      gsa_part_destroy(p);
-      return rc;
+      return rcs[k];
     }
-  *out = p;
+  *out = owner.release();
   return GSA_OK;
 } catch (const std::bad_alloc &) {  // nothing may escape the C ABI
   gsa::set_error("out of host memory", __FILE__, __LINE__);
@@ -806,6 +835,7 @@ int32_t gsa_part_lsm_batch(gsa_part *p, const uint8_t *pats, const uint64_t *pat
   if (Q == 0) return GSA_OK;
   u64 max_len = 0;
   for (u64 q = 0; q < Q; ++q) max_len = std::max(max_len, pat_off[q + 1] - pat_off[q]);
+  std::lock_guard<std::mutex> one_query(p->query_mu);  // ensure_halo() below may replace a shard's text buffer
 
   const size_t nd = p->devices.size();
   struct PerDev {

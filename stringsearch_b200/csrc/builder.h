@@ -22,6 +22,8 @@ int stable_byte_order_device(const u8 *d_bytes, u32 n, u32 *d_order, u32 *d_coun
 // verify.cu
 size_t sufcheck_workspace_bytes(u32 n);
 int sufcheck_device(const u8 *d_T, const i32 *d_SA, u32 n, cudaStream_t st, i64 *bad_index);
+// *bad_slot = first slot whose entry is not in [0, n), or -1.  Synchronises `st`.
+int sa_range_check_device(const i32 *d_SA, u32 n, cudaStream_t st, i64 *bad_slot);
 
 // bwt.cu
 int bwt_device(const u8 *d_T, const i32 *d_SA, u32 n, u8 *d_U, i32 *primary_index, cudaStream_t st);

@@ -25,34 +25,43 @@ def sort_in_place(text, sa: np.ndarray, device: int | None = None, stats: N.Buil
     t = N.as_u8(text)
     if not (isinstance(sa, np.ndarray) and sa.dtype == np.int32 and sa.flags.c_contiguous and sa.flags.writeable):
         raise TypeError("sa must be a writable C-contiguous int32 ndarray")
-    assert t.size == sa.size, "text and suffix array should have same len"
-    assert t.size < I32_MAX, f"text too large, should not exceed {I32_MAX - 1} bytes"
+    # the reference's assert!s (they guard the buffers the library writes, so they are raised
+    # explicitly: a bare `assert` disappears under python -O)
+    if t.size != sa.size:
+        raise AssertionError("text and suffix array should have same len")
+    if t.size >= I32_MAX:
+        raise AssertionError(f"text too large, should not exceed {I32_MAX - 1} bytes")
     if device is None and stats is None:
         rc = N.lib.gsa_divsufsort(N.ptr(t) if t.size else N.ptr(np.zeros(1, np.uint8)),
                                   N.ptr(sa) if sa.size else N.ptr(np.zeros(1, np.int32)), t.size)
     else:
         rc = N.lib.gsa_divsufsort_ex(N.ptr(t) if t.size else N.ptr(np.zeros(1, np.uint8)),
                                      N.ptr(sa) if sa.size else N.ptr(np.zeros(1, np.int32)), t.size,
-                                     0 if device is None else device, C.byref(stats) if stats is not None else None)
-    assert rc == 0, f"divsufsort returned {rc}: {N.last_error()}"  # cdivsufsort lib.rs:22 assert_eq!(0, ret)
+                                     N.current_device() if device is None else device,
+                                     C.byref(stats) if stats is not None else None)
+    if rc != 0:  # cdivsufsort lib.rs:22 assert_eq!(0, ret)
+        raise AssertionError(f"divsufsort returned {rc}: {N.last_error()}")
 
 
 def sort(text, device: int | None = None, stats: N.BuildStats | None = None) -> SuffixArray:
     """-> sacabase.SuffixArray (text borrowed, sa owned), like divsufsort::sort (lib.rs:25-29)."""
     t = N.as_u8(text)
     sa = np.zeros(t.size, dtype=np.int32)
-    sort_in_place(t, sa, device=device, stats=stats)
-    return SuffixArray(t, sa)
+    dev = N.current_device() if device is None else int(device)  # one device for the build and the resident index
+    sort_in_place(t, sa, device=dev, stats=stats)
+    return SuffixArray(t, sa, device=dev)
 
 
 def bwt(text):
     """divbwt (crates/cdivsufsort/c-sources/divsufsort.c:372-405): -> (U, primary_index)."""
     t = N.as_u8(text)
-    assert t.size < I32_MAX, f"text too large, should not exceed {I32_MAX - 1} bytes"
+    if t.size >= I32_MAX:
+        raise AssertionError(f"text too large, should not exceed {I32_MAX - 1} bytes")
     u = np.empty(t.size, dtype=np.uint8)
     rc = N.lib.gsa_divbwt(N.ptr(t) if t.size else N.ptr(np.zeros(1, np.uint8)),
                           N.ptr(u) if u.size else N.ptr(np.zeros(1, np.uint8)), None, t.size)
-    assert rc >= 0, f"divbwt returned {rc}: {N.last_error()}"
+    if rc < 0:
+        raise AssertionError(f"divbwt returned {rc}: {N.last_error()}")
     return u, rc
 
 
@@ -73,10 +82,11 @@ def lcp(text, sa, device: int | None = None) -> np.ndarray:
     (No counterpart in the reference)"""
     t = N.as_u8(text)
     s = np.ascontiguousarray(sa, dtype=np.int32)
-    assert s.size == t.size, "sa and text must have the same length"
+    if s.size != t.size:
+        raise ValueError("sa and text must have the same length")
     out = np.zeros(t.size, dtype=np.int32)
     if t.size:
-        rc = N.lib.gsa_lcp(N.ptr(t), N.ptr(s), N.ptr(out), t.size, 0 if device is None else device)
+        rc = N.lib.gsa_lcp(N.ptr(t), N.ptr(s), N.ptr(out), t.size, N.current_device() if device is None else device)
         if rc != 0:
             raise N.GsaError(rc, "gsa_lcp", N.last_error())
     return out
@@ -86,11 +96,13 @@ def sort_with_lcp(text, device: int | None = None):
     """-> (SuffixArray, LCP) from one call: the text is uploaded once and the suffix array never
     leaves the device between the two steps."""
     t = N.as_u8(text)
-    assert t.size < I32_MAX, f"text too large, should not exceed {I32_MAX - 1} bytes"
+    if t.size >= I32_MAX:
+        raise AssertionError(f"text too large, should not exceed {I32_MAX - 1} bytes")
     sa = np.zeros(t.size, dtype=np.int32)
     out = np.zeros(t.size, dtype=np.int32)
+    dev = N.current_device() if device is None else int(device)
     if t.size:
-        rc = N.lib.gsa_divsufsort_lcp(N.ptr(t), N.ptr(sa), N.ptr(out), t.size, 0 if device is None else device)
+        rc = N.lib.gsa_divsufsort_lcp(N.ptr(t), N.ptr(sa), N.ptr(out), t.size, dev)
         if rc != 0:
             raise N.GsaError(rc, "gsa_divsufsort_lcp", N.last_error())
-    return SuffixArray(t, sa), out
+    return SuffixArray(t, sa, device=dev), out

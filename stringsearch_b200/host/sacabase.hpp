@@ -144,7 +144,7 @@ class SuffixArray : public StringIndex {
   gsa_index *handle() const {
     if (!dev_) {
       gsa_index *h = nullptr;
-      gsa_check(gsa_index_from_parts(text_, sa_.data(), (int64_t)text_len_, device_, &h), "gsa_index_from_parts");
+      gsa_check(gsa_index_from_parts(text_, (int64_t)text_len_, sa_.data(), (int64_t)sa_.size(), device_, &h), "gsa_index_from_parts");
       dev_.reset(h);
     }
     return dev_.get();

@@ -62,8 +62,13 @@ class _DeviceIndex:
 class SuffixArray(StringIndex):
     """sacabase::SuffixArray<'a, i32> (lib.rs:152-197)."""
 
-    def __init__(self, text, sa: np.ndarray, device: int = 0):
-        """SuffixArray::new(text, sa) (lib.rs:170-172): takes ownership of `sa`."""
+    def __init__(self, text, sa: np.ndarray, device: int | None = None):
+        """SuffixArray::new(text, sa) (lib.rs:170-172): takes ownership of `sa`.
+
+        `device`: where the resident copy used by the queries and by verify() lives (None = the
+        current CUDA device at the time of the first query).  The copy is made lazily; a suffix
+        array whose length differs from the text's, or with an entry that is no text position, is
+        refused there (ValueError / IndexError) instead of being read out of bounds."""
         self._text = N.as_u8(text)
         self._sa = np.ascontiguousarray(sa, dtype=np.int32)
         self._device = device
@@ -136,9 +141,15 @@ class SuffixArray(StringIndex):
     # -- plumbing -------------------------------------------------------------------------
     def _handle(self):
         if self._dev is None:
+            if self._sa.size != self._text.size:
+                raise ValueError(f"text and suffix array should have same len ({self._text.size} != {self._sa.size})")
             h = C.c_void_p()
-            rc = N.lib.gsa_index_from_parts(N.ptr(self._text), N.ptr(self._sa), self._text.size, self._device, C.byref(h))
+            dev = N.current_device() if self._device is None else int(self._device)
+            rc = N.lib.gsa_index_from_parts(N.ptr(self._text), self._text.size, N.ptr(self._sa), self._sa.size, dev, C.byref(h))
+            if rc == N.GSA_EPANIC:
+                raise IndexError(f"index out of bounds: {N.last_error()}")  # lib.rs:53-57 slices text[sa[x]..]
             N.check(rc, "gsa_index_from_parts")
+            self._device = dev
             self._dev = _DeviceIndex(h)
         return self._dev.h
 

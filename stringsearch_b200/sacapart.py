@@ -118,6 +118,7 @@ class DistributedPartitionedSuffixArray(StringIndex):
         self._ps, self._np = partition_plan(self._text.size, num_partitions)
         self._halo = halo
         self._shards = []  # (partition index, offset, handle)
+        self.build_ms = []  # device time of every local shard build (gsa_build_stats.ms_total), in shard order
         for i in range(self.rank, self._np, self.world):
             off = i * self._ps
             ln = min(self._ps, self._text.size - off)
@@ -128,9 +129,11 @@ class DistributedPartitionedSuffixArray(StringIndex):
     # implementation has no such path.
     def _build_shard(self, off: int, ln: int):
         h = C.c_void_p()
+        st = N.BuildStats()
         rc = N.lib.gsa_index_create_shard(N.ptr(self._text), self._text.size, off, ln, self._halo, self._device,
-                                          C.byref(h), None)
+                                          C.byref(h), C.byref(st))
         N.check(rc, "gsa_index_create_shard")
+        self.build_ms.append(float(st.ms_total))
         return h
 
     def _answer_local(self, t_pat, t_off, q, t_start, t_len, dev, max_len: int = 0) -> None:
@@ -158,24 +161,38 @@ class DistributedPartitionedSuffixArray(StringIndex):
         Returns (start, len) numpy arrays on every rank."""
         import torch
 
-        dist = self._dist
         if self._np == 0:
             raise RuntimeError("partitioned suffix arrays should always find at least one longest common substring")
+        dev = torch.device("cuda", self._device) if torch.cuda.is_available() else torch.device("cpu")
+        t_pat = t_off = None
+        if self.rank == src:
+            flat, off = N.pack_patterns(needles)
+            t_off = torch.from_numpy(off.astype(np.int64)).to(dev)
+            t_pat = torch.from_numpy(flat if flat.size else np.zeros(1, np.uint8)).to(dev)
+        t_start, t_len = self.longest_substring_match_device(t_pat, t_off, src)
+        return t_start.cpu().numpy().astype(np.uint64), t_len.cpu().numpy().astype(np.uint32)
+
+    def longest_substring_match_device(self, t_pat, t_off, src: int = 0):
+        """The fan-out query on device tensors (collective).  On rank `src`: `t_pat` uint8 pattern
+        bytes, `t_off` int64 offsets [Q + 1], both on this rank's GPU; ignored elsewhere.  Steps:
+        broadcast of the batch, every rank answers for its shards in ascending partition order
+        (offset / may_extend / strict-greater: gsa_lsm_device), all-gather of the per-rank
+        (start, len) sets, merge on the device (gsa_lsm_reduce_device; lib.rs:86-92).
+        Returns (start int64 [Q], len int32 [Q]) device tensors, identical on every rank."""
+        import torch
+
+        dist = self._dist
         on_gpu = torch.cuda.is_available()
         dev = torch.device("cuda", self._device) if on_gpu else torch.device("cpu")
         # ---- broadcast the pattern batch ------------------------------------------------
         if self.rank == src:
-            flat, off = N.pack_patterns(needles)
-            hdr = torch.tensor([off.size - 1, flat.size], dtype=torch.int64, device=dev)
+            hdr = torch.tensor([t_off.numel() - 1, t_pat.numel()], dtype=torch.int64, device=dev)
         else:
             hdr = torch.zeros(2, dtype=torch.int64, device=dev)
         if self.world > 1:
             dist.broadcast(hdr, src=src, group=self._group)
         q, nbytes = int(hdr[0]), int(hdr[1])
-        if self.rank == src:
-            t_off = torch.from_numpy(off.astype(np.int64)).to(dev)
-            t_pat = torch.from_numpy(flat if flat.size else np.zeros(1, np.uint8)).to(dev)
-        else:
+        if self.rank != src:
             t_off = torch.empty(q + 1, dtype=torch.int64, device=dev)
             t_pat = torch.empty(max(1, nbytes), dtype=torch.uint8, device=dev)
         if self.world > 1:
@@ -205,8 +222,8 @@ class DistributedPartitionedSuffixArray(StringIndex):
             else:  # gloo CPU tests of the plumbing only (no shards can exist without a GPU)
                 s, l = merge_results(g_start.view(self.world, q).numpy().astype(np.uint64),
                                      g_len.view(self.world, q).numpy().astype(np.uint32))
-                return s, l
-        return t_start.cpu().numpy().astype(np.uint64), t_len.cpu().numpy().astype(np.uint32)
+                t_start, t_len = torch.from_numpy(s.astype(np.int64)), torch.from_numpy(l.astype(np.int32))
+        return t_start, t_len
 
     def longest_substring_match(self, needle) -> LongestCommonSubstring:
         s, l = self.longest_substring_match_batch([needle])
@@ -289,20 +306,33 @@ class ReplicatedSuffixArray(StringIndex):
     def _split_and_gather(self, needles, src: int, what: str):
         import torch
 
+        dev = torch.device("cuda", self._device) if torch.cuda.is_available() else torch.device("cpu")
+        t_pat = t_off = None
+        if self.rank == src:
+            flat, off = N.pack_patterns(needles)
+            t_off = torch.from_numpy(off.astype(np.int64)).to(dev)
+            t_pat = torch.from_numpy(flat if flat.size else np.zeros(1, np.uint8)).to(dev)
+        a, b = self.query_device(t_pat, t_off, what, src)
+        return a.cpu().numpy(), b.cpu().numpy()
+
+    def query_device(self, t_pat, t_off, what: str = "lsm", src: int = 0):
+        """One query batch on device tensors (collective).  On rank `src`: `t_pat` uint8 pattern
+        bytes and `t_off` int64 offsets [Q + 1] on this rank's GPU; ignored elsewhere.  The batch is
+        broadcast, rank r answers needles [r * ceil(Q / W), (r + 1) * ceil(Q / W)) against its copy
+        of the index, and one all-gather per result array puts the answers together.
+        what = "lsm" -> (start int64 [Q], len int32 [Q]); "search_all" -> (left int32, count int32)."""
+        import torch
+
         dist = self._dist
         dev = torch.device("cuda", self._device) if torch.cuda.is_available() else torch.device("cpu")
         if self.rank == src:
-            flat, off = N.pack_patterns(needles)
-            hdr = torch.tensor([off.size - 1, flat.size], dtype=torch.int64, device=dev)
+            hdr = torch.tensor([t_off.numel() - 1, t_pat.numel()], dtype=torch.int64, device=dev)
         else:
             hdr = torch.zeros(2, dtype=torch.int64, device=dev)
         if self.world > 1:
             dist.broadcast(hdr, src=src, group=self._group)
         q, nbytes = int(hdr[0]), int(hdr[1])
-        if self.rank == src:
-            t_off = torch.from_numpy(off.astype(np.int64)).to(dev)
-            t_pat = torch.from_numpy(flat if flat.size else np.zeros(1, np.uint8)).to(dev)
-        else:
+        if self.rank != src:
             t_off = torch.empty(q + 1, dtype=torch.int64, device=dev)
             t_pat = torch.empty(max(1, nbytes), dtype=torch.uint8, device=dev)
         if self.world > 1:
@@ -328,7 +358,7 @@ class ReplicatedSuffixArray(StringIndex):
             dist.all_gather_into_tensor(g_start, t_start, group=self._group)
             dist.all_gather_into_tensor(g_len, t_len, group=self._group)
             t_start, t_len = g_start, g_len
-        return t_start[:q].cpu().numpy(), t_len[:q].cpu().numpy()
+        return t_start[:q], t_len[:q]
 
     def longest_substring_match(self, needle) -> LongestCommonSubstring:
         s, l = self.longest_substring_match_batch([needle])

@@ -329,6 +329,50 @@ def test_verify_method_and_notsorted(port):
         sacabase.SuffixArray(t, bad).verify()
 
 
+def test_notsorted_names_the_pair_the_reference_names(port):
+    """sacabase::verify returns the FIRST adjacent pair that is out of order (lib.rs:143-147); the O(n)
+    rank criterion alone would flag (0, 1) here, whose own order is fine."""
+    from stringsearch_b200 import sacabase
+
+    with pytest.raises(sacabase.NotSorted) as e:
+        sacabase.SuffixArray(b"abac", np.array([0, 2, 3, 1], np.int32)).verify()
+    assert (e.value.i, e.value.j) == (2, 3)
+    rng = np.random.default_rng(12)
+    for _ in range(40):
+        n = int(rng.integers(2, 200))
+        t = rng.integers(0, 3, n, dtype=np.uint8).tobytes()
+        sa = port.sa_build(t)
+        i, j = sorted(rng.integers(0, n, 2))
+        if i == j:
+            continue
+        sa[i], sa[j] = sa[j], sa[i]
+        rc, bad = port.verify(t, sa)
+        assert rc == 1
+        with pytest.raises(sacabase.NotSorted) as e:
+            sacabase.SuffixArray(t, sa).verify()
+        assert e.value.i == bad, (t, sa.tolist(), e.value.i, bad)
+
+
+def test_user_supplied_sa_is_range_checked():
+    """SuffixArray::new(text, sa) with an entry that is no text position: the reference panics on its slice
+    bounds check (lib.rs:53-57); here the upload refuses it instead of searching out of bounds."""
+    from stringsearch_b200 import sacabase
+
+    for bad_entry in (6, 2**31 - 1, -1):
+        sa = np.array([5, 3, 1, 0, bad_entry, 2], np.int32)
+        with pytest.raises(IndexError):
+            sacabase.SuffixArray(b"banana", sa).longest_substring_match(b"nan")
+
+
+def test_sort_keeps_build_and_index_on_one_device():
+    from stringsearch_b200 import divsufsort
+
+    s = divsufsort.sort(b"mississippi", device=0)
+    assert s._device == 0
+    s.verify()
+    assert divsufsort.sort(b"mississippi")._device is not None
+
+
 def test_concurrent_builds_from_threads(port):
     """The ABI is re-entrant: sacapart calls its builder from several threads
     (crates/sacapart/src/lib.rs:41,45-49)."""
@@ -342,49 +386,76 @@ def test_concurrent_builds_from_threads(port):
         _assert_same(g, port.sa_build(t), "threaded")
 
 
+def _ref_sa_in_background(ref, t):
+    """Start the reference's C divsufsort (oracle/_ref, 1 thread; ctypes releases the GIL) on `t`
+    and return a function that waits for its SA."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    ex = ThreadPoolExecutor(1)
+    fut = ex.submit(ref.sa_build, t)
+
+    def wait():
+        try:
+            return fut.result()
+        finally:
+            ex.shutdown(wait=False)
+
+    return wait
+
+
+def _full_size_case(ref, t, what, min_rounds=0):
+    """Build on the GPU through the device ABI and through the host-pointer ABI, and compare BOTH,
+    every slot, with the reference's own C libdivsufsort run on the same bytes; the O(n) GPU
+    sufcheck stays as a second, independent check."""
+    import torch
+    from stringsearch_b200 import _native as N
+
+    wait_ref = _ref_sa_in_background(ref, t)
+    n = int(t.size)
+    d_t = torch.from_numpy(t).cuda()
+    d_sa = torch.empty(n, dtype=torch.int32, device="cuda")
+    stats = N.BuildStats()
+    stream = torch.cuda.current_stream().cuda_stream
+    assert N.lib.gsa_build_device(d_t.data_ptr(), d_sa.data_ptr(), n, None, 0, stream, C.byref(stats)) == 0, N.last_error()
+    bad = C.c_int64(-1)
+    assert N.lib.gsa_sufcheck_device(d_t.data_ptr(), d_sa.data_ptr(), n, stream, C.byref(bad)) == 0, bad.value
+    assert stats.rounds >= min_rounds
+    sa_dev = d_sa.cpu().numpy()
+    del d_t, d_sa
+    torch.cuda.empty_cache()
+    sa_host = np.empty(n, dtype=np.int32)
+    assert N.lib.gsa_divsufsort(t.ctypes.data, sa_host.ctypes.data, n) == 0, N.last_error()  # the drop-in call
+    exp = wait_ref()
+    _assert_same(sa_dev, exp, f"{what}: gsa_build_device vs reference C divsufsort")
+    _assert_same(sa_host, exp, f"{what}: gsa_divsufsort vs reference C divsufsort")
+    print(what, stats.ms_total, "ms", [(r["depth"], r["live"], r["passes"]) for r in stats.rounds_list()])
+
+
 @pytest.mark.timeout(900)
-def test_full_size_rand_256M_properties():
-    """BASELINE config 1 at full size: SA of 256 MiB random bytes.  Checked by size-independent
-    properties: O(n) GPU sufcheck (permutation + local order), and byte-exact agreement with the
-    reference on a 16 MiB prefix-independent sample is covered above at smaller n."""
-    import torch
+def test_full_size_rand_256M_bit_exact(ref):
+    """BASELINE config "SA of 256 MiB uniform-random bytes on 1 B200, bit-exact vs cdivsufsort":
+    all 2^28 slots are compared with the reference's C library (crates/cdivsufsort/src/lib.rs:9-30)."""
     from stringsearch_b200 import synth
-    from stringsearch_b200 import _native as N
 
-    t = synth.random_bytes(1 << 28, 2)
-    d_t = torch.from_numpy(t).cuda()
-    d_sa = torch.empty(t.size, dtype=torch.int32, device="cuda")
-    stats = N.BuildStats()
-    stream = torch.cuda.current_stream().cuda_stream
-    assert N.lib.gsa_build_device(d_t.data_ptr(), d_sa.data_ptr(), t.size, None, 0, stream, C.byref(stats)) == 0
-    bad = C.c_int64(-1)
-    assert N.lib.gsa_sufcheck_device(d_t.data_ptr(), d_sa.data_ptr(), t.size, stream, C.byref(bad)) == 0, bad.value
-    # spot check: the first and last 1000 slots really are sorted suffixes (host memcmp)
-    sa = d_sa.cpu().numpy()
-    for lo in (0, t.size - 1001):
-        for j in range(lo, lo + 1000):
-            a, b = int(sa[j]), int(sa[j + 1])
-            assert t[a:a + 64].tobytes() <= t[b:b + 64].tobytes()
-    print("rand_256M", stats.ms_total, "ms", [(r["depth"], r["live"], r["passes"]) for r in stats.rounds_list()])
+    _full_size_case(ref, synth.random_bytes(1 << 28, 2), "rand_256M")
 
 
-@pytest.mark.timeout(1200)
-def test_full_size_rep_1G_properties():
-    """BASELINE config 2 at full size: 1 GiB period-1000 text with mutations (many rounds)."""
-    import torch
+@pytest.mark.timeout(1500)
+def test_full_size_rep_1G_bit_exact(ref):
+    """BASELINE config "SA of 1 GiB highly repetitive text" at full size (period 1000, 1e-3
+    mutations, many doubling rounds): all 2^30 slots against the reference's C library."""
     from stringsearch_b200 import synth
-    from stringsearch_b200 import _native as N
 
-    t = synth.repetitive(1 << 30, 3)
-    d_t = torch.from_numpy(t).cuda()
-    d_sa = torch.empty(t.size, dtype=torch.int32, device="cuda")
-    stats = N.BuildStats()
-    stream = torch.cuda.current_stream().cuda_stream
-    assert N.lib.gsa_build_device(d_t.data_ptr(), d_sa.data_ptr(), t.size, None, 0, stream, C.byref(stats)) == 0
-    bad = C.c_int64(-1)
-    assert N.lib.gsa_sufcheck_device(d_t.data_ptr(), d_sa.data_ptr(), t.size, stream, C.byref(bad)) == 0, bad.value
-    assert stats.rounds >= 10
-    print("rep_1G", stats.ms_total, "ms", [(r["depth"], r["live"], r["passes"]) for r in stats.rounds_list()])
+    _full_size_case(ref, synth.repetitive(1 << 30, 3), "rep_1G", min_rounds=10)
+
+
+@pytest.mark.timeout(900)
+def test_full_size_acgt_shard_bit_exact(ref):
+    """One shard of BASELINE config "PartitionedSuffixArray of 4 GiB input, 8 x 512 MiB shards":
+    chunk = 2^32 / 8 + 1 = 536 870 913 bytes of ACGT (crates/sacapart/src/lib.rs:43)."""
+    from stringsearch_b200 import synth
+
+    _full_size_case(ref, synth.acgt(536870913, 4), "acgt_512M_shard")
 
 
 @pytest.mark.timeout(1800)

@@ -195,3 +195,51 @@ def test_header_is_plain_c99(tmp_path):
     r = subprocess.run(["/usr/bin/gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-I", os.path.join(ROOT, "include"),
                         "-fsyntax-only", str(src)], capture_output=True, text=True)
     assert r.returncode == 0 and not r.stderr.strip(), r.stderr
+
+
+def test_memory_safety_preconditions_are_not_asserts():
+    """Checks that guard buffers handed to the library must survive `python -O` and bad offsets."""
+    from stringsearch_b200 import _native as N, divsufsort, sacabase
+
+    src = open(os.path.join(ROOT, "stringsearch_b200", "divsufsort.py")).read()
+    assert not re.search(r"^\s*assert ", src, flags=re.M), "bare assert statements vanish under python -O"
+    with pytest.raises(AssertionError):
+        divsufsort.sort_in_place(b"abc", np.zeros(2, np.int32))
+    with pytest.raises(ValueError):
+        divsufsort.lcp(b"abc", np.zeros(2, np.int32))
+    flat = np.frombuffer(b"abcdef", np.uint8)
+    with pytest.raises(ValueError):
+        N.pack_patterns((flat, np.array([0, 3, 9], np.uint64)))       # runs past the pattern bytes
+    with pytest.raises(ValueError):
+        N.pack_patterns((flat, np.array([0, 4, 2], np.uint64)))       # not monotone
+    N.pack_patterns((flat, np.array([0, 3, 6], np.uint64)))
+    # SuffixArray::new with a suffix array of another length is refused before anything is uploaded
+    with pytest.raises(ValueError):
+        sacabase.SuffixArray(b"banana", np.array([5, 3, 1], np.int32)).longest_substring_match(b"an")
+    h = C.c_void_p()
+    t = np.frombuffer(b"banana", np.uint8)
+    sa = np.array([5, 3, 1, 0, 4, 2], np.int32)
+    assert N.lib.gsa_index_from_parts(N.ptr(t), 6, N.ptr(sa), 5, 0, C.byref(h)) == N.GSA_EINVAL
+
+
+def test_bench_part_4g_text_is_synth_acgt():
+    """bench.py fills the 4 GiB text of BASELINE configs[3] chunk by chunk: same bytes as synth.acgt(n, 4)."""
+    from stringsearch_b200 import synth
+
+    n, step = (1 << 20) + 8, 1 << 18
+    rng = np.random.default_rng(4)
+    b = np.empty(n, np.uint8)
+    for lo in range(0, n, step):
+        b[lo:lo + step] = synth._ACGT[rng.integers(0, 4, min(step, n - lo), dtype=np.uint8)]
+    assert (b == synth.acgt(n, 4)).all()
+
+
+def test_bench_whole_build_formula():
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    rounds = [dict(live=100, sorted=100, passes=4, bag=0), dict(live=90, sorted=10, passes=7, bag=5)]
+    assert bench.whole_build_bytes(rounds) == 100 * (41 + 96) + 8 * 90 + (44 + 168) * 10 + 32 * 5
+    assert bench.config_of("rep_1G", 1) == bench.config_of("rep_1G", 1) and bench.config_of("rep_1G", 1)["bytes_per_gpu"] == 1 << 30
