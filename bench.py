@@ -49,7 +49,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 MB = 1e6
-CPU_SAMPLE_BYTES = 256 << 20   # bounded sample of a 1 GiB workload for the CPU arms (~13-15 s per build)
+CPU_SAMPLE_BYTES = 256 << 20   # bounded sample of a 1 GiB workload for our arm's cpu_baseline (one build, ~20 s)
+REF_SAMPLE_BYTES = 128 << 20   # ... and for each of the K timed steps of --impl reference (~10 s per step)
 CPU_WARMUP_BYTES = 32 << 20    # CPU warm-up steps only page the library and buffers in
 PART_N, PART_P = 1 << 32, 8    # BASELINE configs[3]
 QUERY_N, QUERY_Q, QUERY_M = 1 << 30, 10_000_000, 32  # BASELINE configs[4]
@@ -244,7 +245,7 @@ def run_reference(args, rank, world):
         # each step a bounded sample: the first CPU_SAMPLE_BYTES / 4 of every chunk
         text = synth.acgt(PART_N, 4)
         ps = PART_N // PART_P + 1
-        per = min(ps, CPU_SAMPLE_BYTES // 4)
+        per = min(ps, REF_SAMPLE_BYTES // 4)
         full = [text[i * ps:min(PART_N, (i + 1) * ps)] for i in range(PART_P)]
         samples = [np.ascontiguousarray(c[:per]) for c in full]
         threads = min(PART_P, cores)
@@ -255,7 +256,7 @@ def run_reference(args, rank, world):
 
         with ThreadPoolExecutor(min(n_gpus, cores)) as ex:  # the texts of the N ranks (numpy releases the GIL in its generators)
             full = list(ex.map(lambda r: make_workload(args.workload, r), range(n_gpus)))
-        per = min(full[0].size, CPU_SAMPLE_BYTES)
+        per = min(full[0].size, REF_SAMPLE_BYTES)
         samples = [np.ascontiguousarray(t[:per]) for t in full]
         threads = min(n_gpus, cores)
         sample_desc = (f"first {per >> 20} MiB of each rank's {args.workload} input" if per < full[0].size
@@ -263,6 +264,13 @@ def run_reference(args, rank, world):
     warm = [np.ascontiguousarray(s[:CPU_WARMUP_BYTES]) for s in samples]
     for _ in range(args.warmup):
         cpu_reference_build(warm, threads)
+    # the full-size config once (no sampling; N = 1 only, ~2 min): shows what the per-step sample hides
+    full_once = None
+    if args.full_once and n_gpus == 1 and per < full[0].size:
+        secs = cpu_reference_build([np.ascontiguousarray(x) for x in full], threads)
+        full_once = {"bytes": int(sum(x.size for x in full)), "seconds": secs, "value": sum(x.size for x in full) / secs / MB,
+                     "unit": "MB/s", "cores": threads,
+                     "what": "every text of the config at full size, built once (not part of the K timed steps)"}
     t = 0.0
     for _ in range(args.steps):
         t += cpu_reference_build(samples, threads)
@@ -280,12 +288,9 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    # the full-size config once (no sampling), when the budget allows: shows what the sample hides
-    if args.full_once and n_gpus == 1 and per < full[0].size and time.perf_counter() - t_start < 420:
-        secs = cpu_reference_build([np.ascontiguousarray(x) for x in full], threads)
-        out["full_config_once"] = {"bytes": int(sum(x.size for x in full)), "seconds": secs,
-                                   "value": sum(x.size for x in full) / secs / MB, "unit": "MB/s", "cores": threads,
-                                   "what": "every text of the config at full size, built once (not part of the timed steps)"}
+    if full_once is not None:
+        out["full_config_once"] = full_once
+        out["cpu_baseline"]["sample"] += f"; the un-sampled config built once: {full_once['value']:.2f} MB/s (full_config_once)"
     print("\n" + json.dumps(out), flush=True)
     return 0
 
@@ -550,6 +555,7 @@ def bench_part_4g(cx: Ctx, n=PART_N, P=PART_P, Q=2_000_000, m=32, steps=3):
         raise RuntimeError("bench: part_4G query answers violate the match properties")
     psa.close()
     pin.free()
+    N.lib.gsa_release_cached_memory()
     torch.cuda.empty_cache()
     return res
 
@@ -576,7 +582,7 @@ def bench_queries(cx: Ctx, n=QUERY_N, Q=QUERY_Q, m=QUERY_M, steps=3):
         t_off = torch.from_numpy(off.astype(np.int64)).to(cx.dev)
     out = {}
     for what, key, nsteps in (("lsm", "longest_substring_match", 31), ("search_all", "search_all", 60)):
-        rsa.query_device(t_pat, t_off, what)  # warm-up
+        rsa.query_device(t_pat, t_off, what)  # warm-up (also builds the prefix-bucket table of the index)
         cx.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -587,9 +593,35 @@ def bench_queries(cx: Ctx, n=QUERY_N, Q=QUERY_Q, m=QUERY_M, steps=3):
         ms = cx.max_over_ranks(e0.elapsed_time(e1) / steps)
         out[what] = (a, b)
         res[key] = {"queries_per_s": Q / (ms / 1e3), "ms": ms,
-                    "algorithmic_GBps": Q * nsteps * (4 + m) / (ms / 1e3) / 1e9,
-                    "sector_GBps": Q * nsteps * (32 + 64) / (ms / 1e3) / 1e9,
-                    "includes": "pattern broadcast + all-gather of the two result arrays over NCCL" if cx.world > 1 else "kernel only (patterns resident, world 1)"}
+                    "includes": ("pattern broadcast + all-gather of the two result arrays over NCCL" if cx.world > 1 else
+                                 "ReplicatedSuffixArray.query_device at world 1: header / max-length reductions and result allocation around the kernel")}
+        if cx.world == 1:
+            # the kernel alone: patterns, offsets and result arrays resident, one launch per step
+            d_a = torch.empty(Q, dtype=torch.int64 if what == "lsm" else torch.int32, device=cx.dev)
+            d_b = torch.empty(Q, dtype=torch.int32, device=cx.dev)
+
+            def launch():
+                if what == "lsm":
+                    rc = N.lib.gsa_lsm_device(h, t_pat.data_ptr(), t_off.data_ptr(), Q, m, 0, 0, d_a.data_ptr(), d_b.data_ptr(), cx.stream())
+                else:
+                    rc = N.lib.gsa_search_all_device(h, t_pat.data_ptr(), t_off.data_ptr(), Q, m, d_a.data_ptr(), d_b.data_ptr(), cx.stream())
+                if rc != 0:
+                    raise RuntimeError(f"search kernel rc={rc}: {N.last_error()}")
+
+            launch()
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(steps):
+                launch()
+            e1.record()
+            torch.cuda.synchronize()
+            kms = e0.elapsed_time(e1) / steps
+            res[key]["kernel"] = {"queries_per_s": Q / (kms / 1e3), "ms": kms,
+                                  "algorithmic_GBps": Q * nsteps * (4 + m) / (kms / 1e3) / 1e9,
+                                  "sector_GBps": Q * nsteps * (32 + 64) / (kms / 1e3) / 1e9,
+                                  "bytes_model": f"reference walk: {nsteps} steps x (4 B SA entry + {m} B text) per query (SURVEY 8(d)); sector = 32 + 64 B per step",
+                                  "what": "gsa_lsm_device / gsa_search_all_device, everything resident"}
+            assert torch.equal(d_a, a) and torch.equal(d_b, b)
     if cx.rank == 0:
         # host-pointer calls, pinned buffers (H2D of 320 MB patterns + 80 MB offsets, D2H of results inside)
         pb = [N.PinnedBuffer(flat.nbytes), N.PinnedBuffer(off.nbytes), N.PinnedBuffer(8 * Q), N.PinnedBuffer(4 * Q), N.PinnedBuffer(4 * Q)]
@@ -638,6 +670,7 @@ def bench_queries(cx: Ctx, n=QUERY_N, Q=QUERY_Q, m=QUERY_M, steps=3):
     else:
         ok = True
     rsa.close()
+    N.lib.gsa_release_cached_memory()
     torch.cuda.empty_cache()
     if not cx.all_ok(bool(ok)):
         raise RuntimeError("bench: GPU query results differ from the oracle")

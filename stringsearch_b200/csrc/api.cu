@@ -263,6 +263,11 @@ struct gsa_index {
   const u8 *host_full = nullptr;
   u64 n_full = 0;
   u64 offset = 0;
+  // prefix-bucket table of the searches (search.cu), built by the first query on this index
+  std::mutex accel_mu;
+  bool accel_ready = false;
+  AccelView accel{};
+  u32 *d_accel = nullptr;
 };
 
 struct gsa_part {
@@ -545,7 +550,12 @@ static int index_create_impl(const u8 *T_full, u64 n_full, u64 offset, u64 len, 
       }
       return GSA_OK;
     }
-    return build_sa_device(d_T.p, d_SA.p, (u32)len, nullptr, 0, st.s, stats);
+    // the sort workspace comes from the per-device scratch cache (a cudaMalloc / cudaFree pair of ~66 bytes per
+    // text byte costs more than a shard's upload); a concurrent build on the same device gets a block of its own
+    const size_t ws_bytes = build_workspace_bytes((u32)len);
+    Scratch sc;
+    GSA_TRY_RC(sc.acquire(device, ws_bytes));
+    return build_sa_device(d_T.p, d_SA.p, (u32)len, sc.p, sc.bytes, st.s, stats);
   };
   if (rc == GSA_OK) rc = body();
   if (rc != GSA_OK) { delete ix; return rc; }
@@ -605,6 +615,7 @@ void gsa_index_destroy(gsa_index *ix) {
   DeviceGuard dg(ix->device);
   if (ix->d_text) cudaFree(ix->d_text);
   if (ix->d_sa) cudaFree(ix->d_sa);
+  if (ix->d_accel) cudaFree(ix->d_accel);
   delete ix;
 }
 
@@ -627,7 +638,29 @@ static int ensure_halo(gsa_index *ix, u64 want) {
 // ------------------------------------------------------------------------------------------
 // Batched search, host pointers
 // ------------------------------------------------------------------------------------------
-static TextView view_of(const gsa_index *ix) { return TextView{ix->d_text, ix->d_sa, ix->n, ix->text_avail}; }
+// The table is built on first use (index creation stays as cheap as the build itself); the caller has
+// selected the index's device.  The search kernels work without it (k == 0) if the allocation fails.
+static int ensure_accel(const gsa_index *cix) {
+  gsa_index *ix = const_cast<gsa_index *>(cix);
+  std::lock_guard<std::mutex> lk(ix->accel_mu);
+  if (ix->accel_ready) return GSA_OK;
+  DeviceGuard dg(ix->device);
+  if (!dg.ok) return GSA_ECUDA;
+  Stream st;
+  GSA_TRY_RC(st.create());
+  const int rc = accel_build_device(ix->d_text, ix->d_sa, ix->n, 0, &ix->accel, &ix->d_accel, st.s);
+  if (rc == GSA_ENOMEM) {
+    // no memory for the table: the searches work without it (they start at [0, n])
+    memset(&ix->accel, 0, sizeof(ix->accel));
+    ix->d_accel = nullptr;
+  } else if (rc != GSA_OK) {
+    return rc;
+  }
+  ix->accel_ready = true;
+  return GSA_OK;
+}
+
+static TextView view_of(const gsa_index *ix) { return TextView{ix->d_text, ix->d_sa, ix->n, ix->text_avail, ix->accel}; }
 
 struct PatternsOnDevice {
   DevBuf<u8> pats;
@@ -673,6 +706,7 @@ int32_t gsa_lsm_batch(const gsa_index *ix, const uint8_t *pats, const uint64_t *
   DevBuf<u32> d_len;
   GSA_TRY_RC(d_start.alloc((size_t)Q));
   GSA_TRY_RC(d_len.alloc((size_t)Q));
+  GSA_TRY_RC(ensure_accel(ix));
   GSA_TRY_RC(lsm_device(view_of(ix), pd.pats.p, pd.off.p, Q, max_len(pat_off, Q), 0, 0, d_start.p, d_len.p, st.s));
   GSA_TRY(cudaMemcpyAsync(out_start, d_start.p, (size_t)Q * 8, cudaMemcpyDeviceToHost, st.s));
   GSA_TRY(cudaMemcpyAsync(out_len, d_len.p, (size_t)Q * 4, cudaMemcpyDeviceToHost, st.s));
@@ -698,6 +732,7 @@ int32_t gsa_search_all_batch(const gsa_index *ix, const uint8_t *pats, const uin
   DevBuf<i32> d_left, d_count;
   GSA_TRY_RC(d_left.alloc((size_t)Q));
   GSA_TRY_RC(d_count.alloc((size_t)Q));
+  GSA_TRY_RC(ensure_accel(ix));
   GSA_TRY_RC(search_all_device(view_of(ix), pd.pats.p, pd.off.p, Q, max_len(pat_off, Q), d_left.p, d_count.p, st.s));
   GSA_TRY(cudaMemcpyAsync(out_left, d_left.p, (size_t)Q * 4, cudaMemcpyDeviceToHost, st.s));
   GSA_TRY(cudaMemcpyAsync(out_count, d_count.p, (size_t)Q * 4, cudaMemcpyDeviceToHost, st.s));
@@ -724,6 +759,7 @@ int32_t gsa_lsm_device(const gsa_index *ix, const uint8_t *d_pats, const uint64_
                        uint32_t max_pat_len, uint64_t offset, int32_t accumulate, uint64_t *d_io_start,
                        uint32_t *d_io_len, void *stream) {
   if (!ix || (Q > 0 && (!d_pat_off || !d_io_start || !d_io_len))) return GSA_EINVAL;
+  if (Q > 0 && ix->n > 0) GSA_TRY_RC(ensure_accel(ix));
   return lsm_device(view_of(ix), d_pats, d_pat_off, Q, max_pat_len, offset, accumulate, d_io_start, d_io_len,
                     static_cast<cudaStream_t>(stream));
 }
@@ -732,6 +768,7 @@ int32_t gsa_search_all_device(const gsa_index *ix, const uint8_t *d_pats, const 
                               uint32_t max_pat_len, int32_t *d_out_left, int32_t *d_out_count, void *stream) {
   if (!ix || (Q > 0 && (!d_pat_off || !d_out_left || !d_out_count))) return GSA_EINVAL;
   if (ix->n == 0) return GSA_EINVAL;
+  if (Q > 0) GSA_TRY_RC(ensure_accel(ix));
   return search_all_device(view_of(ix), d_pats, d_pat_off, Q, max_pat_len, d_out_left, d_out_count,
                            static_cast<cudaStream_t>(stream));
 }
@@ -863,6 +900,7 @@ int32_t gsa_part_lsm_batch(gsa_part *p, const uint8_t *pats, const uint64_t *pat
     for (size_t i = k; i < p->shards.size(); i += nd) {
       gsa_index *ix = p->shards[i];
       GSA_TRY_RC(ensure_halo(ix, max_len));
+      GSA_TRY_RC(ensure_accel(ix));
       GSA_TRY_RC(lsm_device(view_of(ix), d.pd.pats.p, d.pd.off.p, Q, (u32)std::min<u64>(max_len, 0xffffffffull), ix->offset, first ? 0 : 1, d.start.p, d.len.p,
                             d.st.s));
       first = false;

@@ -38,12 +38,28 @@ int lcp_device(const u8 *d_T, const i32 *d_SA, u32 n, i32 *d_LCP, void *workspac
 // search.cu
 // Text view of an index: the suffix array covers text[0, n); text_avail >= n bytes are
 // readable (halo behind a shard, used only by the may_extend rule).
+// Prefix-bucket table of an index (search.cu, "top of the tree"): with code[] the dense code of every byte
+// value (number of smaller byte values that occur in the text; b bits per code) and
+//   key(S) = the first k symbols of S as a k*b-bit number, zero padded when S is shorter,
+// T[c] = number of suffixes whose key is below c (c = 0 .. 2^(k b)).  Keys are non-decreasing along the
+// suffix array, so the insertion point of a pattern lies in [T[key], T[key + 1]] and a search starts there
+// instead of at [0, n].  k == 0: no table (tiny texts, GSA_NO_ACCEL).
+struct AccelView {
+  const u32 *T;
+  u32 k, b;
+  u32 present[8];  // bitmap of the byte values that occur
+  u8 code[256];
+};
 struct TextView {
   const u8 *text;
   const i32 *sa;
   u64 n;
   u64 text_avail;
+  AccelView ac;
 };
+// Builds the table for (d_T[0, n), d_SA) on the current device; *d_table is cudaMalloc'd (caller frees).
+// bits = upper bound on k * b (0: default).  Synchronises `st`.
+int accel_build_device(const u8 *d_T, const i32 *d_SA, u64 n, u32 bits, AccelView *out, u32 **d_table, cudaStream_t st);
 // max_pat_len: longest pattern of the batch, or 0 if unknown (only picks the lanes-per-pattern variant)
 int lsm_device(const TextView &tv, const u8 *d_pats, const u64 *d_pat_off, u64 Q, u32 max_pat_len, u64 offset,
                int accumulate, u64 *d_io_start, u32 *d_io_len, cudaStream_t st);

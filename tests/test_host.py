@@ -243,3 +243,39 @@ def test_bench_whole_build_formula():
     rounds = [dict(live=100, sorted=100, passes=4, bag=0), dict(live=90, sorted=10, passes=7, bag=5)]
     assert bench.whole_build_bytes(rounds) == 100 * (41 + 96) + 8 * 90 + (44 + 168) * 10 + 32 * 5
     assert bench.config_of("rep_1G", 1) == bench.config_of("rep_1G", 1) and bench.config_of("rep_1G", 1)["bytes_per_gpu"] == 1 << 30
+
+
+def test_accel_model_matches_oracle(port):
+    """The prefix-bucket search (search.cu) restated on the CPU (tests/model_accel.py) gives the oracle's
+    answers -- i.e. the final window of sacabase's narrowing does not depend on the path, and the bucket
+    bounds hold for short needles, needles with bytes that do not occur in the text, NUL bytes, suffixes
+    shorter than the key, and every table width."""
+    from model_accel import Accel
+
+    rng = np.random.default_rng(2024)
+    cases = 0
+    for sigma, n in ((1, 40), (2, 300), (3, 500), (4, 2000), (5, 800), (17, 1500), (256, 3000), (4, 1), (4, 2), (2, 3)):
+        alpha = np.sort(rng.choice(256, size=sigma, replace=False)).astype(np.uint8)
+        if sigma > 1 and rng.random() < 0.5:
+            alpha[0] = 0
+        t = alpha[rng.integers(0, sigma, n)].tobytes()
+        sa = port.sa_build(t)
+        for bits in (1, 2, 5, 8, 12):
+            ac = Accel(t, sa, bits)
+            pats = [b"", t[:1], t[-1:], t[-3:], t, t + b"\x00", bytes([255]), bytes([0]), bytes([alpha[0]]) * 40]
+            for _ in range(60):
+                o, ln = int(rng.integers(0, n)), int(rng.integers(1, 24))
+                p = bytearray(t[o:o + ln])
+                r = rng.random()
+                if r < 0.3 and p:
+                    p[int(rng.integers(0, len(p)))] = int(rng.integers(0, 256))  # maybe a byte that does not occur
+                elif r < 0.4:
+                    p = bytearray(rng.integers(0, 256, ln, dtype=np.uint8).tobytes())
+                pats.append(bytes(p))
+            for p in pats:
+                es, el = port.longest_substring_match(t, sa, p)
+                assert ac.lsm(p) == (es, el), (sigma, n, bits, p, ac.lsm(p), (es, el))
+                cnt, left = port.sa_search(t, sa, p)
+                assert ac.search_all(p) == (left, cnt), (sigma, n, bits, p, ac.search_all(p), (left, cnt))
+                cases += 1
+    assert cases > 3000
