@@ -366,12 +366,13 @@ def timed_builds(cx: Ctx, d_t, d_sa, n, ws, ws_bytes, warmup, steps, sample_cloc
     if sampler:
         sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    r = dict(pass_ms=0.0, pass_elems=0, pass_launches=0, launches=0, rounds=None)
+    r = dict(pass_ms=0.0, pass_elems=0, pass_bytes=0, pass_launches=0, launches=0, rounds=None)
     ev0.record()
     for _ in range(steps):
         step()
         r["pass_ms"] += stats.ms_radix_passes
         r["pass_elems"] += stats.radix_pass_elements
+        r["pass_bytes"] += stats.radix_pass_bytes
         r["pass_launches"] += stats.radix_pass_launches
         r["launches"] += stats.kernel_launches
         r["rounds"] = stats.rounds_list()
@@ -841,7 +842,8 @@ def run_ours(args, rank, local_rank, world):
 
     peak, peak_src = measured_peak_gbs()
     pass_ms, pass_elems, pass_launches = r["pass_ms"], r["pass_elems"], r["pass_launches"]
-    achieved = (pass_elems * 24) / (pass_ms / 1e3) / 1e9 if pass_ms > 0 else 0.0
+    pass_bytes = r["pass_bytes"]  # 12 B read + 12 B written per element and launch; less for the u32-key passes of round 0
+    achieved = pass_bytes / (pass_ms / 1e3) / 1e9 if pass_ms > 0 else 0.0
     traffic = pass_traffic_per_element()
     alg_bytes = whole_build_bytes(r["rounds"])
     out = {
@@ -855,10 +857,12 @@ def run_ours(args, rank, local_rank, world):
         "roofline": {
             "bound": "hbm", "kernel": "k_radix_pass (onesweep LSD pass, u64 key + u32 value)",
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
-            "traffic": traffic[0] * pass_elems / max(1, pass_launches) if traffic else None,
+            "traffic": traffic[0] * pass_bytes / 24.0 / max(1, pass_launches) if traffic else None,
             "traffic_source": traffic[1] if traffic else None,
             "launches": int(pass_launches), "avg_launch_ms": pass_ms / max(1, pass_launches),
-            "algorithmic_bytes_per_launch": 24.0 * pass_elems / max(1, pass_launches), "algorithmic_bytes_formula": "24 B x elements (8+4 read, 8+4 written)",
+            "algorithmic_bytes_per_launch": pass_bytes / max(1, pass_launches),
+            "algorithmic_bytes_formula": "elements x (key + 4 read, key + 4 written): 24 B with u64 keys; round-0 keys of <= 32 bits travel as u32 (16 B, 20 B for the widening last pass); "
+                                         "the key-generating first pass reads bits_per_symbol / 8 B of packed text instead of a pair",
             "share_of_step": pass_ms / ms if ms > 0 else None,
             "whole_build": {"algorithmic_bytes": int(alg_bytes), "achieved": alg_bytes * args.steps / (ms / 1e3) / 1e9,
                             "frac_of_peak": alg_bytes * args.steps / (ms / 1e3) / 1e9 / peak,

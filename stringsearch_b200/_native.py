@@ -51,6 +51,7 @@ class BuildStats(C.Structure):
         ("radix_pass_elements", C.c_uint64),
         ("ms_radix_passes", C.c_float),
         ("kernel_launches", C.c_uint64),
+        ("radix_pass_bytes", C.c_uint64),
         ("round", RoundStat * GSA_MAX_ROUNDS),
     ]
 

@@ -677,18 +677,59 @@ struct PatternsOnDevice {
   }
 };
 
-static u32 max_len(const u64 *pat_off, u64 Q) {
-  u64 m = 0;
-  for (u64 q = 0; q < Q; ++q) m = std::max(m, pat_off[q + 1] - pat_off[q]);
-  return (u32)std::min<u64>(m, 0xffffffffull);
-}
-
 static int check_patterns(const u8 *pats, const u64 *pat_off, u64 Q) {
   if (Q == 0) return GSA_OK;
   if (!pat_off) return GSA_EINVAL;
   if (pat_off[Q] > 0 && !pats) return GSA_EINVAL;
   return GSA_OK;
 }
+
+}  // extern "C" (a template in between)
+
+// Host-pointer batch in chunks of kQueryChunk patterns on two streams: the upload of chunk c + 1 and the
+// download of chunk c - 1 overlap the kernel of chunk c (the three use different engines), the longest
+// pattern of a chunk is found by the CPU while the previous chunk is in flight, and the device buffers come
+// from the per-device scratch cache instead of four cudaMalloc / cudaFree pairs per call.
+// launch(d_pats, d_off_of_chunk, Qc, max_len_of_chunk, d_out_a_of_chunk, d_out_b_of_chunk, stream).
+constexpr u64 kQueryChunk = 1u << 20;
+
+template <typename Launch>
+static int chunked_query(const gsa_index *ix, const u8 *pats, const u64 *pat_off, u64 Q, size_t a_bytes, void *out_a,
+                         void *out_b, Launch launch) {
+  Stream st[2];
+  GSA_TRY_RC(st[0].create());
+  GSA_TRY_RC(st[1].create());
+  const u64 bytes = pat_off[Q];
+  const size_t pat_sz = align_up((size_t)bytes + 64, 256), off_sz = align_up((size_t)(Q + 1) * 8, 256);
+  const size_t a_sz = align_up((size_t)Q * a_bytes, 256), b_sz = align_up((size_t)Q * 4, 256);
+  Scratch sc;
+  GSA_TRY_RC(sc.acquire(ix->device, pat_sz + off_sz + a_sz + b_sz));
+  u8 *d_pats = reinterpret_cast<u8 *>(sc.p);
+  u64 *d_off = reinterpret_cast<u64 *>(sc.p + pat_sz);
+  char *d_a = sc.p + pat_sz + off_sz;
+  char *d_b = d_a + a_sz;
+  // the kernels read whole aligned words: the bytes behind the last pattern are defined (masked out, never compared)
+  GSA_TRY(cudaMemsetAsync(d_pats + bytes, 0, 64, st[0].s));
+  GSA_TRY(cudaStreamSynchronize(st[0].s));
+  u64 k = 0;
+  for (u64 c0 = 0; c0 < Q; c0 += kQueryChunk, ++k) {
+    const u64 c1 = std::min(Q, c0 + kQueryChunk), qc = c1 - c0;
+    cudaStream_t s = st[k & 1].s;
+    const u64 b0 = pat_off[c0], b1 = pat_off[c1];
+    if (b1 > b0) GSA_TRY(cudaMemcpyAsync(d_pats + b0, pats + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, s));
+    GSA_TRY(cudaMemcpyAsync(d_off + c0, pat_off + c0, (size_t)(qc + 1) * 8, cudaMemcpyHostToDevice, s));
+    u64 m = 0;
+    for (u64 q = c0; q < c1; ++q) m = std::max(m, pat_off[q + 1] - pat_off[q]);
+    GSA_TRY_RC(launch(d_pats, d_off + c0, qc, (u32)std::min<u64>(m, 0xffffffffull), d_a + c0 * a_bytes, d_b + c0 * 4, s));
+    GSA_TRY(cudaMemcpyAsync(static_cast<char *>(out_a) + c0 * a_bytes, d_a + c0 * a_bytes, (size_t)qc * a_bytes, cudaMemcpyDeviceToHost, s));
+    GSA_TRY(cudaMemcpyAsync(static_cast<char *>(out_b) + c0 * 4, d_b + c0 * 4, (size_t)qc * 4, cudaMemcpyDeviceToHost, s));
+  }
+  GSA_TRY(cudaStreamSynchronize(st[0].s));
+  GSA_TRY(cudaStreamSynchronize(st[1].s));
+  return GSA_OK;
+}
+
+extern "C" {
 
 int32_t gsa_lsm_batch(const gsa_index *ix, const uint8_t *pats, const uint64_t *pat_off, uint64_t Q,
                       uint64_t *out_start, uint32_t *out_len) {
@@ -698,20 +739,12 @@ int32_t gsa_lsm_batch(const gsa_index *ix, const uint8_t *pats, const uint64_t *
   if (Q == 0) return GSA_OK;
   DeviceGuard dg(ix->device);
   if (!dg.ok) return GSA_ECUDA;
-  Stream st;
-  GSA_TRY_RC(st.create());
-  PatternsOnDevice pd;
-  GSA_TRY_RC(pd.upload(pats, pat_off, Q, st.s));
-  DevBuf<u64> d_start;
-  DevBuf<u32> d_len;
-  GSA_TRY_RC(d_start.alloc((size_t)Q));
-  GSA_TRY_RC(d_len.alloc((size_t)Q));
   GSA_TRY_RC(ensure_accel(ix));
-  GSA_TRY_RC(lsm_device(view_of(ix), pd.pats.p, pd.off.p, Q, max_len(pat_off, Q), 0, 0, d_start.p, d_len.p, st.s));
-  GSA_TRY(cudaMemcpyAsync(out_start, d_start.p, (size_t)Q * 8, cudaMemcpyDeviceToHost, st.s));
-  GSA_TRY(cudaMemcpyAsync(out_len, d_len.p, (size_t)Q * 4, cudaMemcpyDeviceToHost, st.s));
-  GSA_TRY(cudaStreamSynchronize(st.s));
-  return GSA_OK;
+  const TextView tv = view_of(ix);
+  return chunked_query(ix, pats, pat_off, Q, 8, out_start, out_len,
+                       [&](const u8 *dp, const u64 *doff, u64 qc, u32 ml, char *da, char *db, cudaStream_t s) {
+                         return lsm_device(tv, dp, doff, qc, ml, 0, 0, reinterpret_cast<u64 *>(da), reinterpret_cast<u32 *>(db), s);
+                       });
 }
 
 int32_t gsa_search_all_batch(const gsa_index *ix, const uint8_t *pats, const uint64_t *pat_off, uint64_t Q,
@@ -725,19 +758,12 @@ int32_t gsa_search_all_batch(const gsa_index *ix, const uint8_t *pats, const uin
   }
   DeviceGuard dg(ix->device);
   if (!dg.ok) return GSA_ECUDA;
-  Stream st;
-  GSA_TRY_RC(st.create());
-  PatternsOnDevice pd;
-  GSA_TRY_RC(pd.upload(pats, pat_off, Q, st.s));
-  DevBuf<i32> d_left, d_count;
-  GSA_TRY_RC(d_left.alloc((size_t)Q));
-  GSA_TRY_RC(d_count.alloc((size_t)Q));
   GSA_TRY_RC(ensure_accel(ix));
-  GSA_TRY_RC(search_all_device(view_of(ix), pd.pats.p, pd.off.p, Q, max_len(pat_off, Q), d_left.p, d_count.p, st.s));
-  GSA_TRY(cudaMemcpyAsync(out_left, d_left.p, (size_t)Q * 4, cudaMemcpyDeviceToHost, st.s));
-  GSA_TRY(cudaMemcpyAsync(out_count, d_count.p, (size_t)Q * 4, cudaMemcpyDeviceToHost, st.s));
-  GSA_TRY(cudaStreamSynchronize(st.s));
-  return GSA_OK;
+  const TextView tv = view_of(ix);
+  return chunked_query(ix, pats, pat_off, Q, 4, out_left, out_count,
+                       [&](const u8 *dp, const u64 *doff, u64 qc, u32 ml, char *da, char *db, cudaStream_t s) {
+                         return search_all_device(tv, dp, doff, qc, ml, reinterpret_cast<i32 *>(da), reinterpret_cast<i32 *>(db), s);
+                       });
 }
 
 int32_t gsa_contains_batch(const gsa_index *ix, const uint8_t *pats, const uint64_t *pat_off, uint64_t Q,

@@ -87,9 +87,11 @@ __device__ __forceinline__ void hist_add(u32 *shist, u64 key, bool valid, int np
 // ghist[p][256] -> bin_base[p][256] (exclusive scan); sets bit p of *skip_mask when one
 // bin of digit p holds all `total` elements (the pass would be the identity).
 __global__ void __launch_bounds__(RADIX) k_scan_hist(const u32 *__restrict__ ghist, u32 *__restrict__ bin_base,
-                                                     u32 total, u32 *__restrict__ skip_mask) {
+                                                     u32 total, u32 *__restrict__ skip_mask,
+                                                     const u32 *__restrict__ total_ptr = nullptr) {
   __shared__ u32 wsum[RADIX / 32];
   const int p = blockIdx.x, t = threadIdx.x, lane = t & 31, w = t >> 5;
+  if (total_ptr != nullptr) total = *total_ptr;  // element count still on the device (the host has not read it yet)
   const u32 c = ghist[p * RADIX + t];
   if (c == total && total != 0) atomicOr(skip_mask, 1u << p);
   u32 x = c;
@@ -111,9 +113,9 @@ __device__ __forceinline__ u32 st_agg(u32 v) { return v + 1u; }
 __device__ __forceinline__ u32 st_pre(u32 v) { return (v + 1u) | 0x80000000u; }
 
 struct PassArgs {
-  const u64 *keys_in;
+  const void *keys_in;  // u64 or u32 keys (template parameter of the pass kernel)
   const u32 *vals_in;
-  u64 *keys_out;
+  void *keys_out;
   u32 *vals_out;
   u32 n;               // elements
   u32 shift;           // digit = (key >> shift) & 255
@@ -123,12 +125,12 @@ struct PassArgs {
   KeyGen gen;          // GEN only
 };
 
-template <int THREADS, int IPT>
+template <int THREADS, int IPT, typename KOUT = u64>
 struct PassCfg {
   static constexpr int WARPS = THREADS / 32;
   static constexpr int TILE = THREADS * IPT;
   // keys, values, per-warp digit counts (u16: a warp holds at most 32 * IPT elements, a tile offset is below TILE), bin offsets
-  static constexpr size_t SMEM = (size_t)TILE * 8 + (size_t)TILE * 4 + (size_t)WARPS * RADIX * 2 + RADIX * 4;
+  static constexpr size_t SMEM = (size_t)TILE * sizeof(KOUT) + (size_t)TILE * 4 + (size_t)WARPS * RADIX * 2 + RADIX * 4;
 };
 
 // Lanes of the warp whose 8-bit digit equals mine, from 8 ballots (cost independent of the
@@ -144,14 +146,17 @@ __device__ __forceinline__ u32 peers_by_ballot(u32 d) {
   return m;
 }
 
-template <int THREADS, int IPT, bool GEN, int MIN_BLOCKS = 3>
+// KIN / KOUT: width of the keys read and written.  Keys of at most 32 bits (round 0 of a text whose round-0
+// depth is 4 bytes) travel as u32 through all passes but the last one, which widens them for the rebuild:
+// 8 + 16 + ... + 20 bytes per element instead of 12 + 24 + ... + 24.
+template <int THREADS, int IPT, bool GEN, int MIN_BLOCKS = 3, typename KIN = u64, typename KOUT = u64>
 __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_radix_pass(const PassArgs a) {
   static_assert(THREADS >= RADIX && THREADS % 32 == 0, "one thread per bin is assumed");
   static_assert(IPT % 2 == 0 && THREADS * IPT <= 65535, "ranks, counts and tile offsets are kept as u16");
   constexpr int WARPS = THREADS / 32;
   constexpr int TILE = THREADS * IPT;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  u64 *skeys = reinterpret_cast<u64 *>(smem_raw);          // [TILE]
+  KOUT *skeys = reinterpret_cast<KOUT *>(smem_raw);        // [TILE]
   u32 *svals = reinterpret_cast<u32 *>(skeys + TILE);      // [TILE]
   u16 *whist = reinterpret_cast<u16 *>(svals + TILE);      // [WARPS][256] counts -> tile offsets, two per 32-bit word
   u32 *bin_gofs = reinterpret_cast<u32 *>(whist + WARPS * RADIX);  // [256] global offset - local offset
@@ -187,7 +192,8 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_radix_pass(const PassAr
       if (GEN) {
         gen_key0(a.gen, idx, key[k], val[k]);
       } else {
-        key[k] = ld_stream_u64(a.keys_in + idx);
+        if (sizeof(KIN) == 8) key[k] = ld_stream_u64(static_cast<const u64 *>(a.keys_in) + idx);
+        else key[k] = ld_stream_u32(static_cast<const u32 *>(a.keys_in) + idx);
         val[k] = ld_stream_u32(a.vals_in + idx);
       }
     } else {
@@ -281,7 +287,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_radix_pass(const PassAr
   for (int k = 0; k < IPT; ++k) {
     const u32 d = (u32)(key[k] >> a.shift) & 255u;
     const u32 r = wh[d] + ((k & 1) ? (lrank[k >> 1] >> 16) : (lrank[k >> 1] & 0xffffu));
-    skeys[r] = key[k];
+    skeys[r] = (KOUT)key[k];
     svals[r] = val[k];
   }
 
@@ -320,11 +326,275 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_radix_pass(const PassAr
   for (int k = 0; k < IPT; ++k) {
     const u32 e = (u32)k * THREADS + (u32)tid;
     if (e < valid) {
-      const u64 kx = skeys[e];
-      const u32 o = bin_gofs[(u32)(kx >> a.shift) & 255u] + e;
-      a.keys_out[o] = kx;
+      const KOUT kx = skeys[e];
+      const u32 o = bin_gofs[(u32)((u64)kx >> a.shift) & 255u] + e;
+      static_cast<KOUT *>(a.keys_out)[o] = kx;
       a.vals_out[o] = svals[e];
     }
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// k_radix_pass_p: the same onesweep pass as a PERSISTENT kernel whose tiles arrive by bulk
+// asynchronous copies (cp.async.bulk, the 1-D form of TMA; SASS UBLKCP) into a two-deep ring
+// of shared-memory buffers:
+//   * a CTA takes tiles by ticket (atomic counter), so the look-back only ever waits on tiles
+//     that are held by CTAs that are resident and running -- forward progress does not depend
+//     on the order in which the hardware dispatches blocks;
+//   * while tile t is ranked, staged and scattered, the 48 KB of tile t' (the CTA's next
+//     ticket) are already on their way from HBM, signalled through an mbarrier; no warp ever
+//     sits on a global load of keys or values, and the registers hold one tile only while it
+//     is being ranked;
+//   * the buffer a tile was loaded into is reused as its staging area for the scatter.
+// Ticket t + 2 is requested (result unused until the next trip) while t is processed, so the
+// atomic's round trip is off the critical path as well.
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ u32 smem_addr(const void *p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(u64 *bar, u32 count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(u64 *bar, u32 bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void *dst_smem, const void *src_gmem, u32 bytes, u64 *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity) {
+  u32 done;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_addr(bar)), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
+template <int THREADS, int IPT>
+struct PassPCfg {
+  static constexpr int WARPS = THREADS / 32;
+  static constexpr int TILE = THREADS * IPT;
+  static constexpr size_t BUF = (size_t)TILE * 12;  // keys [TILE] then values [TILE]
+  // two tile buffers, per-warp digit counts (u16), bin offsets, two mbarriers
+  static constexpr size_t SMEM = 2 * BUF + (size_t)WARPS * RADIX * 2 + RADIX * 4 + 16;
+};
+
+template <int THREADS, int IPT, bool GEN, int MIN_BLOCKS>
+__global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_radix_pass_p(const PassArgs a, const u32 tiles) {
+  static_assert(THREADS >= RADIX && THREADS % 32 == 0, "one thread per bin is assumed");
+  static_assert(IPT % 2 == 0 && THREADS * IPT <= 65535, "ranks, counts and tile offsets are kept as u16");
+  constexpr int WARPS = THREADS / 32;
+  constexpr int TILE = THREADS * IPT;
+  constexpr size_t BUF = PassPCfg<THREADS, IPT>::BUF;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  u16 *whist = reinterpret_cast<u16 *>(smem_raw + 2 * BUF);           // [WARPS][256] counts -> tile offsets
+  u32 *bin_gofs = reinterpret_cast<u32 *>(whist + WARPS * RADIX);     // [256] global offset - local offset
+  u64 *mbar = reinterpret_cast<u64 *>(bin_gofs + RADIX);              // [2]
+  __shared__ u32 s_wsum[RADIX / 32];
+  __shared__ u32 s_ticket[2];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const u32 lt = lanemask_lt();
+  u16 *wh = whist + warp * RADIX;
+  u32 *wh32 = reinterpret_cast<u32 *>(wh);
+
+  // thread 0: the loader.  issue(t, b): bulk copies of tile t into buffer b, completion on mbar[b]
+  auto issue = [&](u32 t, int b) {
+    const u32 base = t * (u32)TILE;
+    const u32 cnt = min((u32)TILE, a.n - base);
+    const u32 kbytes = (cnt * 8u + 15u) & ~15u, vbytes = (cnt * 4u + 15u) & ~15u;  // the arrays are padded to 256 B
+    unsigned char *buf = smem_raw + (size_t)b * BUF;
+    mbar_expect_tx(&mbar[b], kbytes + vbytes);
+    bulk_load(buf, static_cast<const u64 *>(a.keys_in) + base, kbytes, &mbar[b]);
+    bulk_load(buf + (size_t)TILE * 8, a.vals_in + base, vbytes, &mbar[b]);
+  };
+
+  u32 ahead = 0;  // thread 0: the ticket after the next one (requested early, consumed one trip later)
+  if (tid == 0) {
+    mbar_init(&mbar[0], 1);
+    mbar_init(&mbar[1], 1);
+    fence_mbar_init();
+    s_ticket[0] = atomicAdd(a.counter, 1u);
+  }
+  __syncthreads();
+  u32 tile = s_ticket[0];
+  int cur = 0;
+  u32 parity = 0;  // bit b = phase of mbar[b] to wait for
+  if (tid == 0) {
+    if (!GEN && tile < tiles) issue(tile, 0);
+    ahead = atomicAdd(a.counter, 1u);
+  }
+  while (tile < tiles) {
+    if (tid == 0) {
+      const u32 nt = ahead;
+      s_ticket[cur ^ 1] = nt;
+      if (!GEN && nt < tiles) issue(nt, cur ^ 1);
+      ahead = (nt < tiles) ? atomicAdd(a.counter, 1u) : nt;
+    }
+    for (int i = tid; i < WARPS * RADIX / 2; i += THREADS) reinterpret_cast<u32 *>(whist)[i] = 0;
+    const u32 tile_base = tile * (u32)TILE;
+    const u32 valid = min((u32)TILE, a.n - tile_base);
+    u64 *skeys = reinterpret_cast<u64 *>(smem_raw + (size_t)cur * BUF);
+    u32 *svals = reinterpret_cast<u32 *>(skeys + TILE);
+
+    // ---- the tile: element order is (warp, k, lane) ------------------------------------------
+    u64 key[IPT];
+    u32 val[IPT];
+    if (!GEN) {
+      mbar_wait(&mbar[cur], (parity >> cur) & 1u);
+      parity ^= 1u << cur;
+    }
+    const u32 lbase = (u32)warp * (32u * IPT) + (u32)lane;
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) {
+      const u32 e = lbase + (u32)k * 32u;
+      if (e < valid) {
+        if (GEN) {
+          gen_key0(a.gen, tile_base + e, key[k], val[k]);
+        } else {
+          key[k] = skeys[e];
+          val[k] = svals[e];
+        }
+      } else {
+        key[k] = ~0ull;  // digit 255 at every shift; sits behind every real element of the tile
+        val[k] = 0;
+      }
+    }
+    __syncthreads();  // counts are zero; everybody holds its elements: the buffer becomes the staging area
+
+    // ---- per-warp digit counts and warp-local stable ranks (see k_radix_pass) -----------------
+    u32 lrank[IPT / 2];
+    bool use_match;
+    {
+      const u32 d = (u32)(key[0] >> a.shift) & 255u;
+      const u32 peers = peers_by_ballot(d);
+      const u32 below = __popc(peers & lt);
+      u32 base = 0;
+      if (below == 0) base = (atomicAdd(&wh32[d >> 1], (u32)__popc(peers) << (16u * (d & 1u))) >> (16u * (d & 1u))) & 0xffffu;
+      base = __shfl_sync(0xffffffffu, base, __ffs(peers) - 1);
+      lrank[0] = base + below;
+      use_match = __popc(__ballot_sync(0xffffffffu, below == 0)) <= 6;
+    }
+    if (use_match) {
+#pragma unroll
+      for (int k = 1; k < IPT; ++k) {
+        const u32 d = (u32)(key[k] >> a.shift) & 255u;
+        const u32 peers = __match_any_sync(0xffffffffu, d);
+        const u32 below = __popc(peers & lt);
+        u32 base = 0;
+        if (below == 0) base = (atomicAdd(&wh32[d >> 1], (u32)__popc(peers) << (16u * (d & 1u))) >> (16u * (d & 1u))) & 0xffffu;
+        base = __shfl_sync(0xffffffffu, base, __ffs(peers) - 1);
+        if (k & 1) lrank[k >> 1] |= (base + below) << 16; else lrank[k >> 1] = base + below;
+      }
+    } else {
+#pragma unroll
+      for (int k = 1; k < IPT; ++k) {
+        const u32 d = (u32)(key[k] >> a.shift) & 255u;
+        const u32 peers = peers_by_ballot(d);
+        const u32 below = __popc(peers & lt);
+        u32 base = 0;
+        if (below == 0) base = (atomicAdd(&wh32[d >> 1], (u32)__popc(peers) << (16u * (d & 1u))) >> (16u * (d & 1u))) & 0xffffu;
+        base = __shfl_sync(0xffffffffu, base, __ffs(peers) - 1);
+        if (k & 1) lrank[k >> 1] |= (base + below) << 16; else lrank[k >> 1] = base + below;
+      }
+    }
+    __syncthreads();
+
+    // ---- bin totals, per-warp offsets, exclusive scan over bins; publish the aggregate ----
+    u32 cnt = 0, pub = 0, bin_ex = 0;
+    if (tid < RADIX) {
+#pragma unroll
+      for (int w = 0; w < WARPS; ++w) {
+        const u32 c = whist[w * RADIX + tid];
+        whist[w * RADIX + tid] = (u16)cnt;
+        cnt += c;
+      }
+      pub = cnt - ((tid == RADIX - 1) ? ((u32)TILE - valid) : 0u);  // padding is not data
+      if (tile == 0)
+        st_volatile_u32(a.status + tid, st_pre(pub));
+      else
+        st_volatile_u32(a.status + (size_t)tile * RADIX + tid, st_agg(pub));
+      u32 x = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const u32 y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+      }
+      if (lane == 31) s_wsum[warp] = x;
+      cnt = x - cnt;  // exclusive within the warp
+    }
+    __syncthreads();
+    if (tid < RADIX) {
+      u32 add = 0;
+      for (int i = 0; i < warp; ++i) add += s_wsum[i];
+      const u32 ex = bin_ex = cnt + add;
+#pragma unroll
+      for (int w = 0; w < WARPS; ++w) whist[w * RADIX + tid] = (u16)(whist[w * RADIX + tid] + ex);
+    }
+    __syncthreads();
+
+    // ---- final rank inside the tile; stage in the tile's own buffer -----------------------------
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) {
+      const u32 d = (u32)(key[k] >> a.shift) & 255u;
+      const u32 r = wh[d] + ((k & 1) ? (lrank[k >> 1] >> 16) : (lrank[k >> 1] & 0xffffu));
+      skeys[r] = key[k];
+      svals[r] = val[k];
+    }
+
+    // ---- decoupled look-back: one thread per bin, four predecessors per round trip ------------
+    if (tid < RADIX) {
+      u32 excl = 0;
+      if (tile != 0) {
+        const u32 *base = a.status + tid;
+        i64 t = (i64)tile - 1;
+        const u32 done0 = st_pre(0);
+        for (;;) {
+          u32 sv[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) sv[j] = (t - j >= 0) ? ld_volatile_u32(base + (size_t)(t - j) * RADIX) : done0;
+          int used = 0;
+          bool fin = false;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (!fin && used == j && sv[j] != 0u) {
+              excl += (sv[j] & 0x7fffffffu) - 1u;
+              used = j + 1;
+              fin = (sv[j] & 0x80000000u) != 0u;
+            }
+          }
+          if (fin) break;
+          t -= used;
+        }
+        st_volatile_u32(a.status + (size_t)tile * RADIX + tid, st_pre(excl + pub));
+      }
+      bin_gofs[tid] = a.bin_base[tid] + excl - bin_ex;
+    }
+    __syncthreads();
+
+    // ---- scatter: consecutive threads write consecutive slots of a digit run -----------------
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) {
+      const u32 e = (u32)k * THREADS + (u32)tid;
+      if (e < valid) {
+        const u64 kx = skeys[e];
+        const u32 o = bin_gofs[(u32)(kx >> a.shift) & 255u] + e;
+        static_cast<u64 *>(a.keys_out)[o] = kx;
+        a.vals_out[o] = svals[e];
+      }
+    }
+    fence_proxy_async();  // this buffer is the target of a bulk copy two trips from now
+    __syncthreads();
+    tile = s_ticket[cur ^ 1];
+    cur ^= 1;
   }
 }
 #endif  // __CUDACC__

@@ -407,6 +407,7 @@ __global__ void __launch_bounds__(256) k_huge_rho(const u32 *__restrict__ hl, co
 struct GatherArgs {
   const u32 *lst_in;  // null: candidates are 0..Lin-1
   u32 Lin;
+  const u32 *Lin_ptr;  // non-null: the number of candidates is read from device memory (k_prefilter's output)
   u32 *rank;          // read; members of re-labelled / finalised huge groups rewrite their own entry
   i32 *SA;
   u32 n;
@@ -462,7 +463,8 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_gather(const GatherArgs
   __syncthreads();
   const u32 lt = lanemask_lt();
   const bool anyv = __ldg(a.verdicts) != 0u;
-  const u32 nchunks = (a.Lin + CH - 1) / CH;
+  const u32 Lin = a.Lin_ptr ? __ldg(a.Lin_ptr) : a.Lin;
+  const u32 nchunks = (Lin + CH - 1) / CH;
   for (u32 chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
     // warp w owns the contiguous sub-chunk [w*32*IPT, (w+1)*32*IPT); row k = 32 consecutive candidates
     const u32 wb = chunk * CH + (u32)warp * (32u * IPT) + (u32)lane;
@@ -471,7 +473,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_gather(const GatherArgs
 #pragma unroll
     for (int k = 0; k < IPT; ++k) {
       const u32 c = wb + (u32)k * 32u;
-      sfx[k] = (c < a.Lin) ? (a.lst_in ? __ldg(a.lst_in + c) : c) : 0xffffffffu;
+      sfx[k] = (c < Lin) ? (a.lst_in ? __ldg(a.lst_in + c) : c) : 0xffffffffu;
     }
 #pragma unroll
     for (int k = 0; k < IPT; ++k) {
@@ -588,6 +590,178 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_gather(const GatherArgs
   __syncthreads();
   for (int i = tid; i < a.npass * RADIX; i += THREADS)
     if (shist[i]) atomicAdd(&a.ghist[i], shist[i]);
+}
+
+// ------------------------------------------------------------------------------------
+// Dense rounds (every text position is a candidate, most of them inert members of huge groups):
+// a streaming pre-filter in front of k_gather.  Four consecutive suffixes per thread with 128-bit
+// loads of rank[i..i+3] and rank[i+h..i+h+3]; a suffix that is
+//   * finalised or in the bag                       -> dropped, as k_gather would,
+//   * a member of a huge group that got no verdict this round, whose partner label got none
+//     either and equals the group's rho*            -> INERT: counted as live, 1 in 256 volunteers
+//                                                      as a representative, nothing else happens,
+//   * anything else                                 -> appended to the candidate list that k_gather
+//                                                      then walks with its full logic.
+// k_gather spends ~130 instructions on every candidate; in the first doubling rounds of a
+// repetitive text 75-99 % of all text positions are inert, and this kernel settles them with ~15.
+// A block stages the candidates of its 8192 positions in shared memory and reserves their place
+// in the list with one atomic (the list stays in text order up to the order of the blocks).
+// ------------------------------------------------------------------------------------
+struct PrefilterArgs {
+  const u32 *rank;
+  u32 n;
+  u64 h;
+  u32 round;
+  u32 tiny_max;
+  const u64 *state;
+  const u32 *verdicts;
+  const u64 *rho;
+  u64 *rep;
+  const u32 *hlist;   // labels of this round's huge groups (after k_huge_prepare)
+  const u32 *hcount;
+  u32 *cand;         // out: suffixes that need k_gather's full treatment
+  u32 *cand_count;   // zeroed before launch
+  u32 *counter;      // k_gather's counter word: inert suffixes are added to the live count ([0])
+};
+
+// The per-group look-ups (rho*, verdict) are what bounds a walk in text order: neighbouring suffixes belong to
+// different groups, so a warp's 32 look-ups hit 32 different cache lines of tables that are indexed by label --
+// one L1 wavefront per suffix (ncu: k_gather runs at 81 % of the L1 pipe and 23 % of DRAM).  Every block
+// therefore starts by hashing this round's huge groups into a direct-mapped table in SHARED memory
+// (label -> rho* | verdict bit): 32 look-ups then cost a few bank conflicts.  A group that loses its slot
+// to another one is looked up in the global tables as before.
+constexpr int PF_THREADS = 256, PF_WARPS = PF_THREADS / 32;
+constexpr int PF_ITERS = 4;                        // a warp settles 128 * PF_ITERS consecutive suffixes per reservation
+constexpr int PF_WCHUNK = 128 * PF_ITERS;          // ... and stages at most that many candidates
+constexpr u32 PF_CACHE = 4096, PF_MAX_GROUPS = 2048;  // groups beyond that: no pre-filter (the table would thrash)
+constexpr int PF_BLOCKS_PER_SM = 4;
+constexpr u32 PF_VERDICT = 0x80000000u, PF_NO_RHO = 0x7fffffffu;  // values no label can have
+constexpr size_t PF_SMEM = (size_t)PF_CACHE * 8 + (size_t)PF_WARPS * PF_WCHUNK * 4;
+
+__device__ __forceinline__ u32 pf_slot(u32 lab) { return ((lab >> 8) * 2654435761u) >> 20; }  // 12 bits
+
+__device__ __noinline__ void pf_volunteer(u64 *rep, u32 lab, u32 round, u32 sfx) {
+  const u32 hsh = mix32(sfx ^ (round * 0x9e3779b9u));
+  atomicMin(reinterpret_cast<unsigned long long *>(rep + (lab / HUGE_M) * HUGE_REPS + ((hsh >> 8) & (HUGE_REPS - 1u))),
+            (unsigned long long)rep_key(round, hsh >> 11, sfx));
+}
+
+// Warps work on their own: no block barrier inside the walk, one output reservation per warp and 512 suffixes
+// (none at all when everything was inert), the inert count kept in a register until the end.
+// ANYV: some huge group got a verdict this round (then a partner label that is a live huge label must be
+// looked up as well: it counts only if its group got none).
+template <bool ALIGNED, bool ANYV>
+__device__ __forceinline__ void pf_walk(const PrefilterArgs &a, const unsigned long long *s_cache, u32 *s_stage) {
+  const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const u32 lt = lanemask_lt();
+  u32 *stage = s_stage + warp * PF_WCHUNK;
+  const u32 dead_mask = RANK_DEAD | (a.tiny_max ? 1u : 0u);
+  const u32 vol = a.round & 0xffu;
+  const u32 nwc = (a.n + PF_WCHUNK - 1) / PF_WCHUNK;
+  const u32 wstride = gridDim.x * PF_WARPS;
+  u32 inert = 0;
+  for (u32 wc = blockIdx.x * PF_WARPS + warp; wc < nwc; wc += wstride) {
+    uint4 wv[PF_ITERS], rv[PF_ITERS];
+#pragma unroll
+    for (int it = 0; it < PF_ITERS; ++it) {
+      const u32 i0 = wc * (u32)PF_WCHUNK + (u32)it * 128u + lane * 4u;
+      wv[it] = make_uint4(RANK_DEAD, RANK_DEAD, RANK_DEAD, RANK_DEAD);
+      rv[it] = make_uint4(0, 0, 0, 0);
+      if (i0 + 4u <= a.n) {
+        wv[it] = ld_stream_u128(a.rank + i0);
+      } else {
+        u32 t[4] = {RANK_DEAD, RANK_DEAD, RANK_DEAD, RANK_DEAD};
+        for (int j = 0; j < 4; ++j) if (i0 + j < a.n) t[j] = a.rank[i0 + j];
+        wv[it] = make_uint4(t[0], t[1], t[2], t[3]);
+      }
+      const u64 t0 = (u64)i0 + a.h;
+      if (ALIGNED && t0 + 4u <= a.n) {
+        rv[it] = ld_stream_u128(a.rank + t0);
+      } else {
+        u32 t[4] = {0, 0, 0, 0};
+        for (int j = 0; j < 4; ++j) if (t0 + j < a.n) t[j] = __ldg(a.rank + t0 + j);
+        rv[it] = make_uint4(t[0], t[1], t[2], t[3]);
+      }
+    }
+    u32 nst = 0;  // candidates staged by this warp so far
+#pragma unroll
+    for (int it = 0; it < PF_ITERS; ++it) {
+      const u32 i0 = wc * (u32)PF_WCHUNK + (u32)it * 128u + lane * 4u;
+      const u32 w[4] = {wv[it].x, wv[it].y, wv[it].z, wv[it].w};
+      const u32 r2[4] = {rv[it].x, rv[it].y, rv[it].z, rv[it].w};
+      u32 slow = 0;  // bit j: suffix i0 + j goes to k_gather
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const bool live = !(w[j] & dead_mask) && w[j] != 0u;
+        const unsigned long long ent = s_cache[pf_slot(w[j])];
+        bool is_inert = live && (u32)(ent >> 32) == w[j] && (u32)ent == (r2[j] & RANK_MASK);  // (a cached label is a huge one)
+        if (ANYV) {
+          if (is_inert && needs_state(r2[j])) {
+            const unsigned long long e2 = s_cache[pf_slot(r2[j])];
+            is_inert = (u32)(e2 >> 32) == r2[j] && !((u32)e2 & PF_VERDICT);  // not cached: let k_gather look it up
+          }
+        }
+        if (is_inert) {
+          ++inert;
+          const u32 sfx = i0 + j;
+          if (((sfx * 0x9e3779b1u) >> 24) == vol) pf_volunteer(a.rep, w[j], a.round, sfx);  // same volunteers as k_gather
+        } else if (live) {
+          slow |= 1u << j;
+        }
+      }
+      // stage the slow ones: (lane, j) order = text order inside the warp's 128 positions
+      if (__any_sync(0xffffffffu, slow != 0u)) {
+        u32 before = 0, total = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const u32 b = __ballot_sync(0xffffffffu, (slow >> j) & 1u);
+          before += (u32)__popc(b & lt);
+          total += (u32)__popc(b);
+        }
+        u32 o = nst + before;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if ((slow >> j) & 1u) stage[o++] = i0 + j;
+        nst += total;
+      }
+    }
+    if (nst) {  // warp-uniform
+      u32 base = 0;
+      if (lane == 0) base = atomicAdd(a.cand_count, nst);
+      base = __shfl_sync(0xffffffffu, base, 0);
+      __syncwarp();
+      for (u32 x = lane; x < nst; x += 32u) a.cand[base + x] = stage[x];
+      __syncwarp();
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) inert += __shfl_xor_sync(0xffffffffu, inert, o);
+  if (lane == 0 && inert) atomicAdd(reinterpret_cast<unsigned long long *>(a.counter), (unsigned long long)inert);  // live count, low word
+}
+
+template <bool ALIGNED>
+__global__ void __launch_bounds__(PF_THREADS, PF_BLOCKS_PER_SM) k_prefilter(const PrefilterArgs a) {
+  extern __shared__ __align__(16) unsigned char pf_smem[];
+  unsigned long long *s_cache = reinterpret_cast<unsigned long long *>(pf_smem);  // label << 32 | (rho* or PF_NO_RHO) | PF_VERDICT
+  u32 *s_stage = reinterpret_cast<u32 *>(s_cache + PF_CACHE);                       // [PF_WARPS][PF_WCHUNK]
+  const u32 tid = threadIdx.x;
+  const bool anyv = __ldg(a.verdicts) != 0u;
+  for (u32 i = tid; i < PF_CACHE; i += PF_THREADS) s_cache[i] = 0ull;
+  __syncthreads();
+  {
+    const u32 hc = __ldg(a.hcount);
+    for (u32 j = tid; j < hc; j += PF_THREADS) {
+      const u32 lab = __ldg(a.hlist + j);
+      const u64 e = __ldg(a.rho + (lab / HUGE_M));
+      const bool verdict = anyv && (u32)(__ldg(a.state + (lab / HUGE_M)) >> 32) == a.round;
+      u32 val = ((u32)(e >> 32) == a.round) ? (u32)e : PF_NO_RHO;
+      if (verdict) val = PF_VERDICT | PF_NO_RHO;
+      atomicCAS(&s_cache[pf_slot(lab)], 0ull, ((unsigned long long)lab << 32) | val);  // first come, first served
+    }
+  }
+  __syncthreads();
+  if (anyv) pf_walk<ALIGNED, true>(a, s_cache, s_stage);
+  else pf_walk<ALIGNED, false>(a, s_cache, s_stage);
 }
 
 // Sparse mode, after k_gather: fill in the missing second key halves, then histogram.
@@ -1303,6 +1477,46 @@ __global__ void __launch_bounds__(BAG_THREADS) k_bag_refine(const BagArgs a) {
   }
 }
 
+// One launch instead of a dozen memsets: zero the counters selected by `mask` (bit w = word w of the
+// counter block) and the digit histograms.
+__global__ void __launch_bounds__(256) k_round_reset(u32 *__restrict__ ctr, u64 mask, u32 *__restrict__ ghist) {
+  const u32 t = threadIdx.x;
+  if (t < 64 && ((mask >> t) & 1ull)) ctr[t] = 0;
+  for (u32 i = t; i < MAX_PASSES * RADIX; i += 256) ghist[i] = 0;
+}
+
+// A round that sorts at most SMALL_SORT elements does so in one block (bitonic network in shared
+// memory, ordered by (key, suffix)) instead of launching up to eight radix passes, each with its
+// look-back status reset: the late rounds of most texts sort a handful of suffixes, and there
+// the launches are the cost.
+constexpr u32 SMALL_SORT = 2048;
+__global__ void __launch_bounds__(1024) k_small_sort(u64 *__restrict__ keys, u32 *__restrict__ vals, u32 S) {
+  __shared__ u64 sk[SMALL_SORT];
+  __shared__ u32 sv[SMALL_SORT];
+  const u32 t = threadIdx.x;
+  for (u32 i = t; i < SMALL_SORT; i += 1024) {
+    sk[i] = (i < S) ? keys[i] : ~0ull;
+    sv[i] = (i < S) ? vals[i] : 0xffffffffu;  // padding sorts behind every real element
+  }
+  __syncthreads();
+  for (u32 k = 2; k <= SMALL_SORT; k <<= 1) {
+    for (u32 j = k >> 1; j > 0; j >>= 1) {
+      for (u32 i = t; i < SMALL_SORT; i += 1024) {
+        const u32 x = i ^ j;
+        if (x > i) {
+          const bool up = (i & k) == 0;
+          const u64 ka = sk[i], kb = sk[x];
+          const u32 va = sv[i], vb = sv[x];
+          const bool gt = ka > kb || (ka == kb && va > vb);
+          if (gt == up) { sk[i] = kb; sk[x] = ka; sv[i] = vb; sv[x] = va; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (u32 i = t; i < S; i += 1024) { keys[i] = sk[i]; vals[i] = sv[i]; }
+}
+
 // ------------------------------------------------------------------------------------
 // Host driver
 // ------------------------------------------------------------------------------------
@@ -1337,8 +1551,9 @@ struct Layout {
   u64 *hkt_keys; u32 *hkt_labels; u32 hkt_cap;  // round-0 key -> label of the huge groups
   u32 *hfull;                  // [256] window histogram of round 0
   u32 *hlist[2]; u32 hcap;     // labels of the huge groups
-  u32 *hcount;                 // [2]
-  u32 *gupd; u32 *gupd_count;  // end-of-inert-block updates of one round
+  u32 *ctr;                    // [64] every counter the host reads back, in one block (one copy per sync point)
+  u32 *hcount;                 // ctr + 4: [0], [1] entries of the two huge lists, [2] verdict flag of the round
+  u32 *gupd; u32 *gupd_count;  // end-of-inert-block updates of one round (count: ctr + 16)
   u32 *tile_rtail, *next_rtail;
   u32 *ghist;      // [MAX_PASSES][256]
   u32 *bin_base;   // [MAX_PASSES][256]
@@ -1374,18 +1589,19 @@ Layout make_layout(char *base, u32 n) {
   y.hfull = c.take<u32>(RADIX);
   y.hcap = (u32)(2 * (N / HUGE_T) + 4096);
   y.hlist[0] = c.take<u32>(y.hcap); y.hlist[1] = c.take<u32>(y.hcap);
-  y.hcount = c.take<u32>(64);
+  y.ctr = c.take<u32>(64);
+  y.hcount = y.ctr + 4;
   y.gupd = c.take<u32>(3 * (size_t)y.hcap);
-  y.gupd_count = c.take<u32>(64);
+  y.gupd_count = y.ctr + 16;
   y.lst[0] = c.take<u32>(N);  y.lst[1] = c.take<u32>(N);
   y.rank = c.take<u32>(N);
   y.ghist = c.take<u32>(MAX_PASSES * RADIX);
   y.bin_base = c.take<u32>(MAX_PASSES * RADIX);
   y.present = c.take<u32>(256);
-  y.skip_mask = c.take<u32>(64);
-  y.live_counter = c.take<u32>(64);
-  y.survivors = c.take<u32>(64);
-  const size_t ptiles = div_up(N, 3072);  // smallest tile of the pass configurations
+  y.skip_mask = y.ctr + 10;
+  y.live_counter = y.ctr + 8;   // 64-bit word (live, to sort); ctr + 12: candidates of the pre-filter
+  y.survivors = y.ctr + 14;
+  const size_t ptiles = div_up(N, 2048);  // smallest tile of the pass configurations
   y.pass_status_words = 256 + ptiles * RADIX;
   y.pass_status = c.take<u32>(y.pass_status_words);
   const size_t rtiles = div_up(N, RB_TILE);
@@ -1396,7 +1612,7 @@ Layout make_layout(char *base, u32 n) {
   y.tile_rtail = c.take<u32>(rtiles + 1);
   y.next_rtail = c.take<u32>(rtiles + 1);
   for (int i = 0; i < 2; ++i) { y.bag_sufx[i] = c.take<u32>(N); y.bag_pos[i] = c.take<u32>(N); }
-  y.bag_count = c.take<u32>(64);
+  y.bag_count = y.ctr + 0;
   y.total = c.used;
   return y;
 }
@@ -1434,25 +1650,44 @@ struct PassTimer {
   }
 };
 
+// Launch of the persistent pass: as many CTAs as fit on the device at once (never more than tiles).
+template <int THREADS, int IPT, bool GEN, int MIN_BLOCKS>
+static void launch_pass_p(const PassArgs &a, u32 L, cudaStream_t st) {
+  static int per_sm = 0, sms = 0;  // (benign race: every thread computes the same values)
+  const int smem = (int)PassPCfg<THREADS, IPT>::SMEM;
+  if (per_sm == 0) {
+    cudaFuncSetAttribute(k_radix_pass_p<THREADS, IPT, GEN, MIN_BLOCKS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    int dev = 0, n = 0, b = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_radix_pass_p<THREADS, IPT, GEN, MIN_BLOCKS>, THREADS, smem);
+    sms = n > 0 ? n : kDefaultSMs;
+    per_sm = b > 0 ? b : 1;
+  }
+  const u32 tiles = (u32)div_up(L, THREADS * IPT);
+  const u32 grid = std::min<u32>(tiles, (u32)(sms * per_sm));
+  k_radix_pass_p<THREADS, IPT, GEN, MIN_BLOCKS><<<grid, THREADS, smem, st>>>(a, tiles);
+}
+
 // Runs the radix passes for digits [0, npass) on `L` elements whose histograms are already
 // in y.ghist.  `cur` is the buffer index holding the input (ignored when gen != null: the
 // first pass then generates the keys and writes buffer 0).  *cur_out = buffer holding the
-// sorted pairs.
+// sorted pairs.  k_scan_hist (bin offsets + constant digits) has been launched by the caller.
 static int run_passes(const Layout &y, u32 L, int npass, int cur, const KeyGen *gen, cudaStream_t st,
-                      gsa_build_stats *stats, PassTimer &timer, int *cur_out, u32 *passes_done) {
-  GSA_TRY(cudaMemsetAsync(y.skip_mask, 0, sizeof(u32), st));
-  k_scan_hist<<<npass, RADIX, 0, st>>>(y.ghist, y.bin_base, L, y.skip_mask);
-  KLAUNCH_CHECK();
-  u32 skip = 0;
-  GSA_TRY(cudaMemcpyAsync(&skip, y.skip_mask, sizeof(u32), cudaMemcpyDeviceToHost, st));
-  GSA_TRY(cudaStreamSynchronize(st));
+                      gsa_build_stats *stats, PassTimer &timer, int *cur_out, u32 *passes_done, u32 skip) {
+  // `skip`: bit p = digit p is the same in every key (k_scan_hist), its pass would be the identity
   const u32 tiles = (u32)div_up(L, PASS_TILE);
   const size_t smem = PassCfg<PASS_THREADS, PASS_IPT>::SMEM;
   const char *cfg_env = getenv("GSA_PASS_CFG");  // experiments: alternative tile shapes of the pass kernel
   const int pass_cfg = cfg_env ? atoi(cfg_env) : 0;
-  const u32 tiles_max = (u32)div_up(L, 3072);
+  const u32 tiles_max = (u32)div_up(L, 2048);
   bool need_gen = gen != nullptr;
   u32 done = 0;
+  // passes that will run; round-0 keys of at most 32 bits travel as u32 between the first and the last of them
+  int last_exec = -1, n_exec = 0;
+  for (int p = 0; p < npass; ++p)
+    if (!(((skip >> p) & 1u) && !(gen != nullptr && n_exec == 0 && p == npass - 1))) { last_exec = p; ++n_exec; }
+  const bool narrow = gen != nullptr && gen->key_bits <= 32 && n_exec >= 2 && pass_cfg == 0 && !getenv("GSA_NO_NARROW");
   for (int p = 0; p < npass; ++p) {
     if (((skip >> p) & 1u) && !(need_gen && p == npass - 1)) continue;  // constant digit: identity pass
     GSA_TRY(cudaMemsetAsync(y.pass_status, 0, (256 + (size_t)(pass_cfg ? tiles_max : tiles) * RADIX) * sizeof(u32), st));
@@ -1470,7 +1705,10 @@ static int run_passes(const Layout &y, u32 L, int npass, int cur, const KeyGen *
       a.keys_in = nullptr; a.vals_in = nullptr;
       a.keys_out = y.keys[0]; a.vals_out = y.vals[0];
       a.gen = *gen;
-      k_radix_pass<PASS_THREADS, PASS_IPT, true><<<tiles, PASS_THREADS, smem, st>>>(a);
+      if (pass_cfg == 10) launch_pass_p<512, 8, true, 2>(a, L, st);
+      else if (pass_cfg == 11) launch_pass_p<256, 16, true, 2>(a, L, st);
+      else if (narrow) k_radix_pass<PASS_THREADS, PASS_IPT, true, 3, u64, u32><<<tiles, PASS_THREADS, PassCfg<PASS_THREADS, PASS_IPT, u32>::SMEM, st>>>(a);
+      else k_radix_pass<PASS_THREADS, PASS_IPT, true><<<tiles, PASS_THREADS, smem, st>>>(a);
       cur = 0;
       need_gen = false;
     } else {
@@ -1483,6 +1721,18 @@ static int run_passes(const Layout &y, u32 L, int npass, int cur, const KeyGen *
         k_radix_pass<384, 16, false, 2><<<(u32)div_up(L, 384 * 16), 384, PassCfg<384, 16>::SMEM, st>>>(a);
       } else if (pass_cfg == 3) {
         k_radix_pass<512, 12, false, 2><<<(u32)div_up(L, 512 * 12), 512, PassCfg<512, 12>::SMEM, st>>>(a);
+      } else if (pass_cfg == 10) {
+        launch_pass_p<512, 8, false, 2>(a, L, st);
+      } else if (pass_cfg == 11) {
+        launch_pass_p<256, 16, false, 2>(a, L, st);
+      } else if (pass_cfg == 12) {
+        launch_pass_p<384, 6, false, 3>(a, L, st);
+      } else if (pass_cfg == 13) {
+        launch_pass_p<256, 8, false, 4>(a, L, st);
+      } else if (narrow && p == last_exec) {
+        k_radix_pass<PASS_THREADS, PASS_IPT, false, PASS_MIN_BLOCKS, u32, u64><<<tiles, PASS_THREADS, smem, st>>>(a);
+      } else if (narrow) {
+        k_radix_pass<PASS_THREADS, PASS_IPT, false, PASS_MIN_BLOCKS, u32, u32><<<tiles, PASS_THREADS, PassCfg<PASS_THREADS, PASS_IPT, u32>::SMEM, st>>>(a);
       } else {
         k_radix_pass<PASS_THREADS, PASS_IPT, false, PASS_MIN_BLOCKS><<<tiles, PASS_THREADS, smem, st>>>(a);
       }
@@ -1494,6 +1744,11 @@ static int run_passes(const Layout &y, u32 L, int npass, int cur, const KeyGen *
     if (stats) {
       stats->radix_pass_launches++;
       stats->radix_pass_elements += L;
+      {
+        const bool was_gen = gen != nullptr && done == 1;
+        const u64 kin = was_gen ? 0 : ((narrow) ? 4 : 8), kout = (narrow && p != last_exec) ? 4 : 8;
+        stats->radix_pass_bytes += (u64)L * (was_gen ? 0 : kin + 4) + (was_gen ? (u64)L * gen->b / 8 : 0) + (u64)L * (kout + 4);
+      }
       stats->kernel_launches++;
     }
   }
@@ -1511,8 +1766,13 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
   {
     // opt in to > 48 KB dynamic shared memory (idempotent, per device)
     const int smem = (int)PassCfg<PASS_THREADS, PASS_IPT>::SMEM;
+    GSA_TRY(cudaFuncSetAttribute(k_prefilter<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PF_SMEM));
+    GSA_TRY(cudaFuncSetAttribute(k_prefilter<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PF_SMEM));
     GSA_TRY(cudaFuncSetAttribute(k_radix_pass<PASS_THREADS, PASS_IPT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     GSA_TRY(cudaFuncSetAttribute(k_radix_pass<PASS_THREADS, PASS_IPT, false, PASS_MIN_BLOCKS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    GSA_TRY(cudaFuncSetAttribute(k_radix_pass<PASS_THREADS, PASS_IPT, true, 3, u64, u32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    GSA_TRY(cudaFuncSetAttribute(k_radix_pass<PASS_THREADS, PASS_IPT, false, PASS_MIN_BLOCKS, u32, u64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    GSA_TRY(cudaFuncSetAttribute(k_radix_pass<PASS_THREADS, PASS_IPT, false, PASS_MIN_BLOCKS, u32, u32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     GSA_TRY(cudaFuncSetAttribute(k_radix_pass<256, 12, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PassCfg<256, 12>::SMEM));
     GSA_TRY(cudaFuncSetAttribute(k_radix_pass<384, 16, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PassCfg<384, 16>::SMEM));
     GSA_TRY(cudaFuncSetAttribute(k_radix_pass<512, 12, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PassCfg<512, 12>::SMEM));
@@ -1632,8 +1892,30 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
   int cur = 0;
   u32 passes = 0;
   PassTimer timer;
+  // Host <-> device traffic of the control flow: every counter the host needs lives in one 64-word block
+  // (y.ctr), read back with ONE copy per sync point (`mailbox`); the counters of a round are zeroed by one
+  // kernel.  Sync points per doubling round: after the gather (how much is live / to be sorted, which digits
+  // are constant) and at the end (survivors, bag, huge groups); large rounds add one before the rebuild (is
+  // this the last round?), small ones do not bother.
+  u32 mailbox[64];
+  auto fetch_counters = [&]() -> int {
+    GSA_TRY(cudaMemcpyAsync(mailbox, y.ctr, sizeof(mailbox), cudaMemcpyDeviceToHost, st));
+    GSA_TRY(cudaStreamSynchronize(st));
+    return GSA_OK;
+  };
+  constexpr u32 SYNC_WORTH = 1u << 20;  // below this many elements an extra host round trip costs more than it can save
+  GSA_TRY(cudaMemsetAsync(y.ctr, 0, 64 * sizeof(u32), st));
   GSA_TRY(cudaEventRecord(ev[1], st));
-  GSA_TRY_RC(run_passes(y, n, npass0, 0, &gen, st, stats, timer, &cur, &passes));
+  {
+    u32 skip0 = 0;
+    k_scan_hist<<<npass0, RADIX, 0, st>>>(y.ghist, y.bin_base, n, y.skip_mask);
+    KLAUNCH_CHECK();
+    if (n >= SYNC_WORTH) {  // a constant digit (a^n ...) saves a pass over all n suffixes
+      GSA_TRY_RC(fetch_counters());
+      skip0 = mailbox[10];
+    }
+    GSA_TRY_RC(run_passes(y, n, npass0, 0, &gen, st, stats, timer, &cur, &passes, skip0));
+  }
   GSA_TRY(cudaEventRecord(ev[2], st));
 
   // key = label(i) << 32 | label(i + h).  The label half starts on a digit boundary on purpose:
@@ -1646,18 +1928,16 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
   GSA_TRY(cudaMemsetAsync(y.state, 0, ((size_t)n / HUGE_M + 2) * sizeof(u64), st));
   GSA_TRY(cudaMemsetAsync(y.rho, 0, ((size_t)n / HUGE_M + 2) * sizeof(u64), st));
   GSA_TRY(cudaMemsetAsync(y.seen, 0, ((size_t)n / HUGE_M + 2) * sizeof(u32), st));
-  GSA_TRY(cudaMemsetAsync(y.hcount, 0, 2 * sizeof(u32), st));
   GSA_TRY(cudaMemsetAsync(y.rep, 0xff, ((size_t)n / HUGE_M + 2) * HUGE_REPS * sizeof(u64), st));
-  // tail summaries + survivor count, then the rebuild proper.  *survivors_out is known before the
-  // rebuild is launched, which lets the last round skip its rank writes.
+  // tail summaries + survivor count, then the rebuild proper.  When the survivor count is fetched before
+  // the rebuild is launched, the last round can skip its rank writes.
   // The bag is off in sparse mode (most suffixes then carry no label at all).
   u32 tiny_conf = getenv("GSA_NO_BAG") ? 0u : TINY_MAX;
   if (const char *e = getenv("GSA_TINY_MAX")) tiny_conf = std::min<u32>(TINY_MAX, (u32)atoi(e));
   int bcur = 0;  // bag buffer the rebuild of the current round appends to (= input of the next round)
-  GSA_TRY(cudaMemsetAsync(y.bag_count, 0, 4 * sizeof(u32), st));
-  auto launch_rebuild = [&](bool round0, u32 rnd, u32 L, int kv, bool may_finish, u32 *survivors_out) -> int {
+  auto launch_rebuild = [&](bool round0, u32 rnd, u32 L, int kv, bool may_finish) -> int {
     const u32 tiles = (u32)div_up(L, RB_TILE);
-    GSA_TRY(cudaMemsetAsync(y.survivors, 0, sizeof(u32), st));
+    GSA_TRY(cudaMemsetAsync(y.survivors, 0, sizeof(u32), st));  // (also the probe's / the sparse mode's scratch counter)
     RebuildArgs r;
     r.keys = y.keys[kv]; r.sufx = y.vals[kv];
     r.pos_in = round0 ? nullptr : y.slots;
@@ -1673,23 +1953,26 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
     r.tiny_max = sparse ? 0u : tiny_conf;
     r.bag_desc = y.keys[kv ^ 1];  // the other half of the sort's double buffer is free until the next walk
     r.bag_desc_count = y.bag_count + 2;
-    GSA_TRY(cudaMemsetAsync(y.bag_count + 2, 0, sizeof(u32), st));
     if (round0) k_tail_summary<RB_THREADS, RB_IPT, true><<<tiles, RB_THREADS, 0, st>>>(r);
     else k_tail_summary<RB_THREADS, RB_IPT, false><<<tiles, RB_THREADS, 0, st>>>(r);
     KLAUNCH_CHECK();
     k_tail_scan<<<1, 1024, 0, st>>>(y.tile_tail, y.next_tail, tiles, y.tile_head, y.prev_head);
     KLAUNCH_CHECK();
-    u32 surv = 0, bag_left = 0;
-    GSA_TRY(cudaMemcpyAsync(&surv, y.survivors, sizeof(u32), cudaMemcpyDeviceToHost, st));
-    GSA_TRY(cudaMemcpyAsync(&bag_left, y.bag_count + bcur, sizeof(u32), cudaMemcpyDeviceToHost, st));
-    GSA_TRY(cudaStreamSynchronize(st));
-    *survivors_out = surv;
-    const bool fin = may_finish && surv == 0 && bag_left == 0;  // nothing is live after this round
+    bool fin = false;
+    u32 surv_bound = L;  // survivors <= L
+    if (round0 || L >= SYNC_WORTH) {
+      GSA_TRY_RC(fetch_counters());
+      const u32 surv = mailbox[14], bag_left = mailbox[bcur];
+      surv_bound = surv;
+      fin = may_finish && surv == 0 && bag_left == 0;  // nothing is live after this round
+      if (round0) {
+        // few survivors: do not scatter n ranks for the sake of a handful of look-ups
+        sparse = surv != 0 && (u64)surv * 64 < n && !getenv("GSA_NO_SPARSE");
+        if (sparse) GSA_TRY(cudaMemsetAsync(y.rank, 0, (size_t)n * sizeof(u32), st));
+        r.tiny_max = sparse ? 0u : tiny_conf;
+      }
+    }
     if (round0) {
-      // few survivors: do not scatter n ranks for the sake of a handful of look-ups
-      sparse = surv != 0 && (u64)surv * 64 < n && !getenv("GSA_NO_SPARSE");
-      if (sparse) GSA_TRY(cudaMemsetAsync(y.rank, 0, (size_t)n * sizeof(u32), st));
-      r.tiny_max = sparse ? 0u : tiny_conf;
       if (fin) k_rebuild<RB_THREADS, RB_IPT, true, RB_FINAL><<<tiles, RB_THREADS, 0, st>>>(r);
       else if (sparse) k_rebuild<RB_THREADS, RB_IPT, true, RB_SPARSE><<<tiles, RB_THREADS, 0, st>>>(r);
       else k_rebuild<RB_THREADS, RB_IPT, true, RB_NORMAL><<<tiles, RB_THREADS, 0, st>>>(r);
@@ -1699,38 +1982,31 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
     }
     KLAUNCH_CHECK();
     if (stats) stats->kernel_launches += 3;
-    if (r.tiny_max && surv > 1) {  // at most surv / 2 new tiny groups
-      k_bag_append<<<(u32)div_up(surv / 2, 256), 256, 0, st>>>(r.bag_desc, r.bag_desc_count, d_SA, y.bag_sufx[bcur],
-                                                              y.bag_pos[bcur], y.bag_count + bcur);
+    if (r.tiny_max && surv_bound > 1) {  // at most survivors / 2 new tiny groups
+      k_bag_append<<<(u32)div_up(surv_bound / 2, 256), 256, 0, st>>>(r.bag_desc, r.bag_desc_count, d_SA, y.bag_sufx[bcur],
+                                                                    y.bag_pos[bcur], y.bag_count + bcur);
       KLAUNCH_CHECK();
       if (stats) stats->kernel_launches++;
     }
     return GSA_OK;
   };
 
-  u32 survivors = 0;
   GSA_TRY(cudaMemsetAsync(y.hkt_labels, 0, (size_t)y.hkt_cap * sizeof(u32), st));
-  GSA_TRY_RC(launch_rebuild(true, 0, n, cur, true, &survivors));
-  if (survivors >= HUGE_T) {  // there may be huge groups: if so, label their members in text order
-    u32 hc0 = 0;
-    GSA_TRY(cudaMemcpyAsync(&hc0, y.hcount + hcur, sizeof(u32), cudaMemcpyDeviceToHost, st));
-    GSA_TRY(cudaStreamSynchronize(st));
-    if (hc0) {
-      const u32 blocks = (u32)std::min<u64>((u64)sms * 8, std::max<u64>(1, div_up(n, 256)));
-      k_rank_huge0<<<blocks, 256, 0, st>>>(gen, HugeKeyTable{y.hkt_keys, y.hkt_labels, y.hkt_cap - 1}, n - ns, y.rank);
-      KLAUNCH_CHECK();
-      if (stats) stats->kernel_launches++;
-    }
+  GSA_TRY_RC(launch_rebuild(true, 0, n, cur, true));
+  GSA_TRY_RC(fetch_counters());  // end of round 0: survivors, bag entries, huge groups
+  u32 survivors = mailbox[14];
+  u32 nbag = mailbox[bcur];     // entries of bag buffer bcur
+  u32 hc = mailbox[4 + hcur];   // huge groups entering round 1
+  if (hc) {  // label the members of the huge groups in text order
+    const u32 blocks = (u32)std::min<u64>((u64)sms * 8, std::max<u64>(1, div_up(n, 256)));
+    k_rank_huge0<<<blocks, 256, 0, st>>>(gen, HugeKeyTable{y.hkt_keys, y.hkt_labels, y.hkt_cap - 1}, n - ns, y.rank);
+    KLAUNCH_CHECK();
+    if (stats) stats->kernel_launches++;
   }
   GSA_TRY(cudaEventRecord(ev[3], st));
-  u32 nbag = 0;  // entries of bag buffer bcur
-  GSA_TRY(cudaMemcpyAsync(&nbag, y.bag_count + bcur, sizeof(u32), cudaMemcpyDeviceToHost, st));
-  GSA_TRY(cudaStreamSynchronize(st));
   u32 round = 0;
   auto log_round = [&](u64 depth, u64 live, u32 sorted, u32 groups, u32 kb, u32 np, u32 bag) {
-    const float pass_ms = timer.drain();
     if (!stats) return;
-    stats->ms_radix_passes += pass_ms;
     if (round >= GSA_MAX_ROUNDS) return;
     gsa_round_stat &s = stats->round[round];
     s.depth = depth; s.live = live; s.sorted = sorted; s.groups = groups; s.key_bits = kb; s.passes = np; s.bag = bag;
@@ -1738,6 +2014,8 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
     cudaEventElapsedTime(&s.ms_sort, ev[1], ev[2]);
     stats->rounds = round + 1;
   };
+  GSA_TRY(cudaEventSynchronize(ev[3]));
+  if (stats) stats->ms_radix_passes += timer.drain();
   log_round(k, n, n, 0, key_bits, passes, 0);
 
   // ---- doubling rounds ------------------------------------------------------------------------
@@ -1749,19 +2027,26 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
   const u32 kb = 2 * lab_bits;
   const int npass = (int)div_up(kb, 8);
   const bool filter_allowed = !getenv("GSA_NO_INERT");
+  const bool use_prefilter = !getenv("GSA_NO_PREFILTER");
+  const bool use_small_sort = !getenv("GSA_NO_SMALL_SORT");
   const u32 tiny_max = sparse ? 0u : tiny_conf;
   while (live > 0 || nbag > 0) {
     ++round;
     GSA_TRY(cudaEventRecord(ev[0], st));
-    // huge groups: verdicts for this round, and the list for the next one
-    u32 hc = 0;
-    GSA_TRY(cudaMemcpyAsync(&hc, y.hcount + hcur, sizeof(u32), cudaMemcpyDeviceToHost, st));
-    GSA_TRY(cudaStreamSynchronize(st));
     // at most n / HUGE_T groups survive k_huge_prepare (duplicates dropped) and at most as many are appended by a
     // rebuild, so the list cannot outgrow its 2 n / HUGE_T + 4096 entries; anything else is a bug, not an input
     if (hc >= y.hcap) { set_error("huge-group list overflow", __FILE__, __LINE__); return GSA_ECUDA; }
-    GSA_TRY(cudaMemsetAsync(y.hcount + (hcur ^ 1), 0, sizeof(u32), st));
-    GSA_TRY(cudaMemsetAsync(y.hcount + 2, 0, sizeof(u32), st));
+    const int bin = bcur;
+    bcur ^= 1;
+    // counters of this round: the new huge list, verdict flag, live / sort counts, skip mask, pre-filter candidates,
+    // survivors, inert-block updates, bag descriptors, the bag buffer this round fills; + the digit histograms
+    {
+      const u64 mask = (1ull << (4 + (hcur ^ 1))) | (1ull << 6) | (1ull << 8) | (1ull << 9) | (1ull << 10) | (1ull << 12) |
+                       (1ull << 14) | (1ull << 16) | (1ull << 2) | (1ull << bcur);
+      k_round_reset<<<1, 256, 0, st>>>(y.ctr, mask, y.ghist);
+      KLAUNCH_CHECK();
+    }
+    // huge groups: verdicts for this round, and the list for the next one
     if (hc) {
       k_huge_prepare<<<(u32)div_up(hc, 256), 256, 0, st>>>(y.hlist[hcur], hc, y.G, y.state, y.rep, round, tiny_max, y.hlist[hcur ^ 1], y.hcount + (hcur ^ 1), y.hcount + 2, getenv("GSA_NO_DEDUPE") ? nullptr : y.seen);
       KLAUNCH_CHECK();
@@ -1774,8 +2059,6 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
       KLAUNCH_CHECK();
       if (stats) stats->kernel_launches++;
     }
-    GSA_TRY(cudaMemsetAsync(y.ghist, 0, MAX_PASSES * RADIX * sizeof(u32), st));
-    GSA_TRY(cudaMemsetAsync(y.live_counter, 0, 2 * sizeof(u32), st));
     GatherArgs g;
     g.lst_in = ident ? nullptr : y.lst[lcur];
     g.Lin = Lcand; g.rank = y.rank; g.SA = d_SA; g.n = n; g.h = h; g.lab_bits = lab_bits;
@@ -1791,16 +2074,29 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
     g.gen = gen;
     g.todo = y.slots;  // free until k_slots of this round
     g.todo_count = y.survivors;
-    if (sparse) GSA_TRY(cudaMemsetAsync(y.survivors, 0, sizeof(u32), st));
+    g.Lin_ptr = nullptr;
+    // dense round: settle the inert majority in a streaming pre-filter, k_gather sees only the rest
+    if (ident && !write_list && filter && !sparse && use_prefilter && hc <= PF_MAX_GROUPS) {
+      u32 *cand_count = y.live_counter + 4;
+      PrefilterArgs pf;
+      pf.rank = y.rank; pf.n = n; pf.h = h; pf.round = round; pf.tiny_max = tiny_max;
+      pf.state = y.state; pf.verdicts = y.hcount + 2; pf.rho = y.rho; pf.rep = y.rep;
+      pf.hlist = y.hlist[hcur]; pf.hcount = y.hcount + hcur;
+      pf.cand = y.lst[0]; pf.cand_count = cand_count; pf.counter = y.live_counter;
+      const u32 pblocks = (u32)std::min<u64>((u64)sms * PF_BLOCKS_PER_SM, std::max<u64>(1, div_up(n, PF_WCHUNK * PF_WARPS)));
+      if (h % 4 == 0) k_prefilter<true><<<pblocks, PF_THREADS, PF_SMEM, st>>>(pf);
+      else k_prefilter<false><<<pblocks, PF_THREADS, PF_SMEM, st>>>(pf);
+      KLAUNCH_CHECK();
+      if (stats) stats->kernel_launches++;
+      g.lst_in = y.lst[0];
+      g.Lin_ptr = cand_count;
+    }
     const u32 gblocks = (u32)std::min<u64>((u64)sms * GA_BLOCKS_PER_SM, std::max<u64>(1, div_up(Lcand, GA_THREADS * GA_IPT)));
     k_gather<GA_THREADS, GA_IPT, GA_BLOCKS_PER_SM><<<gblocks, GA_THREADS, 0, st>>>(g);
     KLAUNCH_CHECK();
-    if (stats) stats->kernel_launches++;
+    if (stats) stats->kernel_launches += 2;
     // the bag: refine the tiny groups.  Every label read of the round (k_gather, k_bag_gather) precedes
     // every label write (k_bag_refine, k_rebuild), so all readers see the labels left by the last round.
-    const int bin = bcur;
-    bcur ^= 1;
-    GSA_TRY(cudaMemsetAsync(y.bag_count + bcur, 0, sizeof(u32), st));
     if (nbag) {
       const u32 bb = (u32)std::min<u64>((u64)sms * 8, div_up(nbag, 256));
       k_bag_gather<<<bb, 256, 0, st>>>(y.bag_sufx[bin], nbag, y.rank, y.state, y.hcount + 2, round, h, n, y.slots);
@@ -1813,12 +2109,15 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
       KLAUNCH_CHECK();
       if (stats) stats->kernel_launches += 2;
     }
-    u32 cnt[2] = {0, 0};  // live suffixes found, of which to sort
-    GSA_TRY(cudaMemcpyAsync(cnt, y.live_counter, sizeof(cnt), cudaMemcpyDeviceToHost, st));
-    GSA_TRY(cudaStreamSynchronize(st));
-    const u32 Llive = cnt[0], S = cnt[1];
+    // bin offsets and constant digits from the histogram the gather left behind; the element count is still on the device
+    if (!sparse) {
+      k_scan_hist<<<npass, RADIX, 0, st>>>(y.ghist, y.bin_base, 0, y.skip_mask, y.live_counter + 1);
+      KLAUNCH_CHECK();
+    }
+    GSA_TRY_RC(fetch_counters());
+    const u32 Llive = mailbox[8], S = mailbox[9];
+    u32 skip = mailbox[10];
     passes = 0;
-    survivors = 0;
     GSA_TRY(cudaEventRecord(ev[1], st));
     GSA_TRY(cudaEventRecord(ev[2], st));
     if (S > 0) {
@@ -1826,13 +2125,30 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
         // at most one entry per sorted suffix (S * 64 < n, so the pairs fit in the slot buffer)
         k_lazy_fill<<<(u32)div_up(S, 256), 256, 0, st>>>(gen, d_SA, g.todo, g.todo_count, y.keys[0]);
         KLAUNCH_CHECK();
-        const u32 hb = (u32)std::min<u64>((u64)sms * 4, std::max<u64>(1, div_up(S, HIST_THREADS)));
-        k_hist_keys<HIST_THREADS><<<hb, HIST_THREADS, 0, st>>>(y.keys[0], S, npass, y.ghist);
-        KLAUNCH_CHECK();
-        if (stats) stats->kernel_launches += 2;
+        if (stats) stats->kernel_launches += 1;
+        skip = 0;
+        if (!use_small_sort || S > SMALL_SORT) {
+          const u32 hb = (u32)std::min<u64>((u64)sms * 4, std::max<u64>(1, div_up(S, HIST_THREADS)));
+          k_hist_keys<HIST_THREADS><<<hb, HIST_THREADS, 0, st>>>(y.keys[0], S, npass, y.ghist);
+          KLAUNCH_CHECK();
+          k_scan_hist<<<npass, RADIX, 0, st>>>(y.ghist, y.bin_base, S, y.skip_mask);
+          KLAUNCH_CHECK();
+          if (stats) stats->kernel_launches += 2;
+          if (S >= SYNC_WORTH) {
+            GSA_TRY_RC(fetch_counters());
+            skip = mailbox[10];
+          }
+        }
       }
       GSA_TRY(cudaEventRecord(ev[1], st));
-      GSA_TRY_RC(run_passes(y, S, npass, 0, nullptr, st, stats, timer, &cur, &passes));
+      if (use_small_sort && S <= SMALL_SORT) {
+        k_small_sort<<<1, 1024, 0, st>>>(y.keys[0], y.vals[0], S);
+        KLAUNCH_CHECK();
+        cur = 0;
+        if (stats) stats->kernel_launches++;
+      } else {
+        GSA_TRY_RC(run_passes(y, S, npass, 0, nullptr, st, stats, timer, &cur, &passes, skip));
+      }
       GSA_TRY(cudaEventRecord(ev[2], st));
       // SA slots of the sorted elements from the group tables
       const u32 tiles = (u32)div_up(S, RB_TILE);
@@ -1840,7 +2156,6 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
       sa.keys = y.keys[cur]; sa.S = S; sa.lab_bits = lab_bits; sa.G = y.G; sa.rho = y.rho; sa.round = round;
       sa.filter = filter ? 1 : 0; sa.slots = y.slots;
       sa.tile_rtail = y.tile_rtail; sa.next_rtail = y.next_rtail; sa.tile_rhead = y.tile_head; sa.prev_rhead = y.prev_head; sa.gupd = y.gupd; sa.gupd_count = y.gupd_count;
-      GSA_TRY(cudaMemsetAsync(y.gupd_count, 0, sizeof(u32), st));
       k_run_summary<RB_THREADS, RB_IPT><<<tiles, RB_THREADS, 0, st>>>(sa);
       KLAUNCH_CHECK();
       k_tail_scan<<<1, 1024, 0, st>>>(y.tile_rtail, y.next_rtail, tiles, y.tile_head, y.prev_head);
@@ -1852,16 +2167,18 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
         KLAUNCH_CHECK();
       }
       if (stats) stats->kernel_launches += 4;
-      GSA_TRY_RC(launch_rebuild(false, round, S, cur, Llive == S, &survivors));
+      GSA_TRY_RC(launch_rebuild(false, round, S, cur, Llive == S));
     }
     GSA_TRY(cudaEventRecord(ev[3], st));
-    u32 nbag_next = 0;
-    GSA_TRY(cudaMemcpyAsync(&nbag_next, y.bag_count + bcur, sizeof(u32), cudaMemcpyDeviceToHost, st));
-    GSA_TRY(cudaStreamSynchronize(st));
+    GSA_TRY_RC(fetch_counters());  // end of the round: survivors, the bag, the huge groups of the next round
+    survivors = (S > 0) ? mailbox[14] : 0u;
+    const u32 hc_this = hc;
+    hc = mailbox[4 + hcur];
     h *= 2;
-    log_round(h, Llive, S, hc, kb, passes, nbag);
+    if (stats) stats->ms_radix_passes += timer.drain();
+    log_round(h, Llive, S, hc_this, kb, passes, nbag);
     live = (Llive - S) + survivors;  // inert members + non-unique sorted ones (some of them now in the bag)
-    nbag = nbag_next;
+    nbag = mailbox[bcur];
     if (write_list) {
       lcur ^= 1;
       Lcand = Llive;

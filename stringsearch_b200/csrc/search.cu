@@ -500,7 +500,7 @@ int accel_build_device(const u8 *d_T, const i32 *d_SA, u64 n, u32 bits, AccelVie
   *d_table = nullptr;
   if (n < 4096 || getenv("GSA_NO_ACCEL")) return GSA_OK;  // k == 0: searches start at [0, n]
   if (const char *e = getenv("GSA_ACCEL_BITS")) bits = (u32)atoi(e);
-  if (bits == 0) bits = 24;
+  if (bits == 0) bits = 26;
   // buckets much finer than the text cannot pay: about 16 suffixes per bucket at least
   bits = std::min<u32>(std::min<u32>(bits, 26), std::max<u32>(8, bits_for(n) > 4 ? bits_for(n) - 4 : 8));
 #define ACCEL_MALLOC(ptr, bytes)                                                          \
