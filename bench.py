@@ -842,7 +842,7 @@ def run_ours(args, rank, local_rank, world):
 
     peak, peak_src = measured_peak_gbs()
     pass_ms, pass_elems, pass_launches = r["pass_ms"], r["pass_elems"], r["pass_launches"]
-    pass_bytes = r["pass_bytes"]  # 12 B read + 12 B written per element and launch; less for the u32-key passes of round 0
+    pass_bytes = r["pass_bytes"]  # 12 B read + 12 B written per element and launch (less for the key-generating pass)
     achieved = pass_bytes / (pass_ms / 1e3) / 1e9 if pass_ms > 0 else 0.0
     traffic = pass_traffic_per_element()
     alg_bytes = whole_build_bytes(r["rounds"])
@@ -861,8 +861,8 @@ def run_ours(args, rank, local_rank, world):
             "traffic_source": traffic[1] if traffic else None,
             "launches": int(pass_launches), "avg_launch_ms": pass_ms / max(1, pass_launches),
             "algorithmic_bytes_per_launch": pass_bytes / max(1, pass_launches),
-            "algorithmic_bytes_formula": "elements x (key + 4 read, key + 4 written): 24 B with u64 keys; round-0 keys of <= 32 bits travel as u32 (16 B, 20 B for the widening last pass); "
-                                         "the key-generating first pass reads bits_per_symbol / 8 B of packed text instead of a pair",
+            "algorithmic_bytes_formula": "24 B x elements (8+4 read, 8+4 written); the key-generating first pass of round 0 reads "
+                                         "bits_per_symbol / 8 B of packed text per element instead of a pair (gsa_build_stats.radix_pass_bytes)",
             "share_of_step": pass_ms / ms if ms > 0 else None,
             "whole_build": {"algorithmic_bytes": int(alg_bytes), "achieved": alg_bytes * args.steps / (ms / 1e3) / 1e9,
                             "frac_of_peak": alg_bytes * args.steps / (ms / 1e3) / 1e9 / peak,

@@ -69,8 +69,8 @@ typedef struct gsa_build_stats {
   uint64_t radix_pass_elements; /* sum over pass launches of elements moved */
   float ms_radix_passes;        /* sum of pass kernel time */
   uint64_t kernel_launches;     /* all kernels launched by this build */
-  uint64_t radix_pass_bytes;    /* sum over pass launches of bytes read + written: elements x (key + 4 in, key + 4 out);
-                                   the first round-0 pass reads b/8 bytes of packed text per element instead of a pair */
+  uint64_t radix_pass_bytes;    /* sum over pass launches of bytes read + written: 12 + 12 per element; the first
+                                   round-0 pass generates its keys and reads b/8 bytes of packed text per element instead */
   gsa_round_stat round[GSA_MAX_ROUNDS];
 } gsa_build_stats;
 

@@ -10,8 +10,7 @@ fn main() {
         .flag("arch=compute_100a,code=sm_100a")
         .flag("-std=c++17")
         .flag("-O3")
-        .flag("-lineinfo")
-        .flag("-rdc=true")
+        .flag("-lineinfo") // no -rdc: every kernel lives in the translation unit that launches it, so no device-link step is needed
         .include("../../include")
         .warnings(false);
     for f in &["api.cu", "sa_build.cu", "search.cu", "verify.cu", "bwt.cu", "lcp.cu"] {

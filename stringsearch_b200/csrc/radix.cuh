@@ -146,9 +146,10 @@ __device__ __forceinline__ u32 peers_by_ballot(u32 d) {
   return m;
 }
 
-// KIN / KOUT: width of the keys read and written.  Keys of at most 32 bits (round 0 of a text whose round-0
-// depth is 4 bytes) travel as u32 through all passes but the last one, which widens them for the rebuild:
-// 8 + 16 + ... + 20 bytes per element instead of 12 + 24 + ... + 24.
+// KIN / KOUT: width of the keys read and written (u64 everywhere today).  Moving round-0 keys of <= 32 bits as u32
+// through all passes but the last (8 + 16 + 16 + 20 instead of 12 + 24 + 24 + 24 bytes per element on rep_1G) was
+// measured and changed nothing (round 0: 46.0 -> 46.2 ms, profiles/r2/README.md): the pass is bound by the latency of
+// its ranking / look-back chain at 37 % occupancy, not by bytes.
 template <int THREADS, int IPT, bool GEN, int MIN_BLOCKS = 3, typename KIN = u64, typename KOUT = u64>
 __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_radix_pass(const PassArgs a) {
   static_assert(THREADS >= RADIX && THREADS % 32 == 0, "one thread per bin is assumed");

@@ -638,7 +638,14 @@ constexpr int PF_BLOCKS_PER_SM = 4;
 constexpr u32 PF_VERDICT = 0x80000000u, PF_NO_RHO = 0x7fffffffu;  // values no label can have
 constexpr size_t PF_SMEM = (size_t)PF_CACHE * 8 + (size_t)PF_WARPS * PF_WCHUNK * 4;
 
-__device__ __forceinline__ u32 pf_slot(u32 lab) { return ((lab >> 8) * 2654435761u) >> 20; }  // 12 bits
+__device__ __forceinline__ u32 pf_slot(u32 lab) { return ((lab >> 8) * 2654435761u) >> 20; }   // 12 bits
+__device__ __forceinline__ u32 pf_slot2(u32 lab) { return ((lab >> 8) * 0x85ebca6bu + 0x3c6ef372u) >> 20; }  // second choice
+// entry of `lab`, or one with another tag if the group is not cached (two possible slots: at 1000 groups in 4096
+// slots one in nine would lose a single slot to another group, and all of its members would go the slow way)
+__device__ __forceinline__ unsigned long long pf_lookup(const unsigned long long *s_cache, u32 lab) {
+  const unsigned long long e = s_cache[pf_slot(lab)];
+  return ((u32)(e >> 32) == lab) ? e : s_cache[pf_slot2(lab)];
+}
 
 __device__ __noinline__ void pf_volunteer(u64 *rep, u32 lab, u32 round, u32 sfx) {
   const u32 hsh = mix32(sfx ^ (round * 0x9e3779b9u));
@@ -693,11 +700,11 @@ __device__ __forceinline__ void pf_walk(const PrefilterArgs &a, const unsigned l
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const bool live = !(w[j] & dead_mask) && w[j] != 0u;
-        const unsigned long long ent = s_cache[pf_slot(w[j])];
+        const unsigned long long ent = pf_lookup(s_cache, w[j]);
         bool is_inert = live && (u32)(ent >> 32) == w[j] && (u32)ent == (r2[j] & RANK_MASK);  // (a cached label is a huge one)
         if (ANYV) {
           if (is_inert && needs_state(r2[j])) {
-            const unsigned long long e2 = s_cache[pf_slot(r2[j])];
+            const unsigned long long e2 = pf_lookup(s_cache, r2[j]);
             is_inert = (u32)(e2 >> 32) == r2[j] && !((u32)e2 & PF_VERDICT);  // not cached: let k_gather look it up
           }
         }
@@ -756,7 +763,8 @@ __global__ void __launch_bounds__(PF_THREADS, PF_BLOCKS_PER_SM) k_prefilter(cons
       const bool verdict = anyv && (u32)(__ldg(a.state + (lab / HUGE_M)) >> 32) == a.round;
       u32 val = ((u32)(e >> 32) == a.round) ? (u32)e : PF_NO_RHO;
       if (verdict) val = PF_VERDICT | PF_NO_RHO;
-      atomicCAS(&s_cache[pf_slot(lab)], 0ull, ((unsigned long long)lab << 32) | val);  // first come, first served
+      const unsigned long long entry = ((unsigned long long)lab << 32) | val;
+      if (atomicCAS(&s_cache[pf_slot(lab)], 0ull, entry) != 0ull) atomicCAS(&s_cache[pf_slot2(lab)], 0ull, entry);  // first come, first served
     }
   }
   __syncthreads();
@@ -1683,11 +1691,6 @@ static int run_passes(const Layout &y, u32 L, int npass, int cur, const KeyGen *
   const u32 tiles_max = (u32)div_up(L, 2048);
   bool need_gen = gen != nullptr;
   u32 done = 0;
-  // passes that will run; round-0 keys of at most 32 bits travel as u32 between the first and the last of them
-  int last_exec = -1, n_exec = 0;
-  for (int p = 0; p < npass; ++p)
-    if (!(((skip >> p) & 1u) && !(gen != nullptr && n_exec == 0 && p == npass - 1))) { last_exec = p; ++n_exec; }
-  const bool narrow = gen != nullptr && gen->key_bits <= 32 && n_exec >= 2 && pass_cfg == 0 && !getenv("GSA_NO_NARROW");
   for (int p = 0; p < npass; ++p) {
     if (((skip >> p) & 1u) && !(need_gen && p == npass - 1)) continue;  // constant digit: identity pass
     GSA_TRY(cudaMemsetAsync(y.pass_status, 0, (256 + (size_t)(pass_cfg ? tiles_max : tiles) * RADIX) * sizeof(u32), st));
@@ -1707,7 +1710,6 @@ static int run_passes(const Layout &y, u32 L, int npass, int cur, const KeyGen *
       a.gen = *gen;
       if (pass_cfg == 10) launch_pass_p<512, 8, true, 2>(a, L, st);
       else if (pass_cfg == 11) launch_pass_p<256, 16, true, 2>(a, L, st);
-      else if (narrow) k_radix_pass<PASS_THREADS, PASS_IPT, true, 3, u64, u32><<<tiles, PASS_THREADS, PassCfg<PASS_THREADS, PASS_IPT, u32>::SMEM, st>>>(a);
       else k_radix_pass<PASS_THREADS, PASS_IPT, true><<<tiles, PASS_THREADS, smem, st>>>(a);
       cur = 0;
       need_gen = false;
@@ -1729,10 +1731,6 @@ static int run_passes(const Layout &y, u32 L, int npass, int cur, const KeyGen *
         launch_pass_p<384, 6, false, 3>(a, L, st);
       } else if (pass_cfg == 13) {
         launch_pass_p<256, 8, false, 4>(a, L, st);
-      } else if (narrow && p == last_exec) {
-        k_radix_pass<PASS_THREADS, PASS_IPT, false, PASS_MIN_BLOCKS, u32, u64><<<tiles, PASS_THREADS, smem, st>>>(a);
-      } else if (narrow) {
-        k_radix_pass<PASS_THREADS, PASS_IPT, false, PASS_MIN_BLOCKS, u32, u32><<<tiles, PASS_THREADS, PassCfg<PASS_THREADS, PASS_IPT, u32>::SMEM, st>>>(a);
       } else {
         k_radix_pass<PASS_THREADS, PASS_IPT, false, PASS_MIN_BLOCKS><<<tiles, PASS_THREADS, smem, st>>>(a);
       }
@@ -1744,11 +1742,8 @@ static int run_passes(const Layout &y, u32 L, int npass, int cur, const KeyGen *
     if (stats) {
       stats->radix_pass_launches++;
       stats->radix_pass_elements += L;
-      {
-        const bool was_gen = gen != nullptr && done == 1;
-        const u64 kin = was_gen ? 0 : ((narrow) ? 4 : 8), kout = (narrow && p != last_exec) ? 4 : 8;
-        stats->radix_pass_bytes += (u64)L * (was_gen ? 0 : kin + 4) + (was_gen ? (u64)L * gen->b / 8 : 0) + (u64)L * (kout + 4);
-      }
+      // 12 B read + 12 B written per element; the key-generating first pass of round 0 reads b / 8 B of packed text instead
+      stats->radix_pass_bytes += (gen != nullptr && done == 1) ? (u64)L * gen->b / 8 + (u64)L * 12 : (u64)L * 24;
       stats->kernel_launches++;
     }
   }
@@ -1770,9 +1765,6 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
     GSA_TRY(cudaFuncSetAttribute(k_prefilter<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PF_SMEM));
     GSA_TRY(cudaFuncSetAttribute(k_radix_pass<PASS_THREADS, PASS_IPT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     GSA_TRY(cudaFuncSetAttribute(k_radix_pass<PASS_THREADS, PASS_IPT, false, PASS_MIN_BLOCKS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    GSA_TRY(cudaFuncSetAttribute(k_radix_pass<PASS_THREADS, PASS_IPT, true, 3, u64, u32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    GSA_TRY(cudaFuncSetAttribute(k_radix_pass<PASS_THREADS, PASS_IPT, false, PASS_MIN_BLOCKS, u32, u64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    GSA_TRY(cudaFuncSetAttribute(k_radix_pass<PASS_THREADS, PASS_IPT, false, PASS_MIN_BLOCKS, u32, u32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     GSA_TRY(cudaFuncSetAttribute(k_radix_pass<256, 12, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PassCfg<256, 12>::SMEM));
     GSA_TRY(cudaFuncSetAttribute(k_radix_pass<384, 16, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PassCfg<384, 16>::SMEM));
     GSA_TRY(cudaFuncSetAttribute(k_radix_pass<512, 12, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PassCfg<512, 12>::SMEM));
