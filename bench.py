@@ -514,7 +514,8 @@ def bench_part_4g(cx: Ctx, n=PART_N, P=PART_P, Q=2_000_000, m=32, steps=3):
         off = np.arange(Q + 1, dtype=np.uint64) * np.uint64(m)
         t_pat = torch.from_numpy(flat).to(cx.dev)
         t_off = torch.from_numpy(off.astype(np.int64)).to(cx.dev)
-    psa.longest_substring_match_device(t_pat, t_off)  # warm-up (NCCL channels, halo)
+    for _ in range(2):  # warm-up (NCCL channels, halo, prefix-bucket tables of the shards)
+        psa.longest_substring_match_device(t_pat, t_off)
     cx.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -583,7 +584,8 @@ def bench_queries(cx: Ctx, n=QUERY_N, Q=QUERY_Q, m=QUERY_M, steps=3):
         t_off = torch.from_numpy(off.astype(np.int64)).to(cx.dev)
     out = {}
     for what, key, nsteps in (("lsm", "longest_substring_match", 31), ("search_all", "search_all", 60)):
-        rsa.query_device(t_pat, t_off, what)  # warm-up (also builds the prefix-bucket table of the index)
+        for _ in range(2):  # warm-up (the first call also builds the prefix-bucket table of the index)
+            rsa.query_device(t_pat, t_off, what)
         cx.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -652,14 +654,15 @@ def bench_queries(cx: Ctx, n=QUERY_N, Q=QUERY_Q, m=QUERY_M, steps=3):
         port = oracle.port()
         sa = np.empty(n, dtype=np.int32)
         assert N.lib.gsa_index_sa(h, sa.ctypes.data) == 0
+        nthr = max(1, (os.cpu_count() or 1) // cx.world)  # (torchrun sets OMP_NUM_THREADS=1: ask for the cores explicitly)
         t0 = time.perf_counter()
-        cs, cl = port.lsm_batch(t, sa, (flat, off), threads=0)
+        cs, cl = port.lsm_batch(t, sa, (flat, off), threads=nthr)
         secs_lsm = time.perf_counter() - t0
         t0 = time.perf_counter()
-        c_left, c_cnt = port.search_all_batch(t, sa, (flat, off), threads=0)
+        c_left, c_cnt = port.search_all_batch(t, sa, (flat, off), threads=nthr)
         secs_all = time.perf_counter() - t0
         res["cpu_baseline"] = {"longest_substring_match_queries_per_s": Q / secs_lsm, "search_all_queries_per_s": Q / secs_all,
-                               "cores": port.max_threads(), "kind": "port",
+                               "cores": nthr, "kind": "port",
                                "sample": f"all {Q} patterns, oracle longest_substring_match / sa_search, OpenMP"}
         d_s, d_l = out["lsm"]
         d_left, d_cnt = out["search_all"]
@@ -708,13 +711,14 @@ def parity_gate(cx: Ctx, n=48 << 20, Q=120_000):
     ok = True
     port = oracle.port() if cx.rank == 0 else None
     ref = oracle.ref(ndebug=True) if cx.rank == 0 else None
+    nthr = max(1, (os.cpu_count() or 1) // cx.world)  # (torchrun sets OMP_NUM_THREADS=1)
     for P in (8, 5):
         psa = sacapart.DistributedPartitionedSuffixArray(t, P, cx.local_rank)
         s, l = psa.longest_substring_match_batch(needles if cx.rank == 0 else None)
         psa.close()
         if cx.rank == 0:
             ps, sas = port.part_build(t, P, builder=ref.sa_build)
-            es, el = port.part_lsm_batch(t, ps, sas, needles)
+            es, el = port.part_lsm_batch(t, ps, sas, needles, threads=nthr)
             good = bool((s == es).all() and (l == el).all())
             report[f"partitioned_P{P}"] = "equal" if good else f"{int(((s != es) | (l != el)).sum())} answers differ"
             ok = ok and good
@@ -724,8 +728,8 @@ def parity_gate(cx: Ctx, n=48 << 20, Q=120_000):
     rsa.close()
     if cx.rank == 0:
         sa = ref.sa_build(t)
-        es, el = port.lsm_batch(t, sa, needles)
-        e_left, e_cnt = port.search_all_batch(t, sa, needles)
+        es, el = port.lsm_batch(t, sa, needles, threads=nthr)
+        e_left, e_cnt = port.search_all_batch(t, sa, needles, threads=nthr)
         good = bool((s == es).all() and (l == el).all() and (left == e_left).all() and (cnt == e_cnt).all())
         report["replicated"] = "equal" if good else "answers differ"
         ok = ok and good
@@ -748,10 +752,12 @@ def run_ours(args, rank, local_rank, world):
     if world > 1:
         # stdout carries exactly one JSON line: NCCL's log (kept on: it shows the ranks and the NVLink / NVLS transport)
         # goes to stderr unless the caller routed it elsewhere
-        os.environ.setdefault("NCCL_DEBUG", "INFO")
-        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+        os.environ["NCCL_DEBUG"] = os.environ.get("GSA_NCCL_DEBUG", "INFO")
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT,ENV")
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
+        if rank == 0:
+            log(f"[bench] torch.distributed backend=nccl nranks={dist.get_world_size()} NCCL {'.'.join(map(str, torch.cuda.nccl.version()))}")
 
     if args.workload == "part_4G":
         return run_part_main(cx)

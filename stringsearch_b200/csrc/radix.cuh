@@ -23,7 +23,7 @@ constexpr int RADIX_BITS = 8;
 constexpr int RADIX = 1 << RADIX_BITS;
 constexpr int MAX_PASSES = 8;
 #ifndef GSA_PASS_DYNAMIC_TILES
-#define GSA_PASS_DYNAMIC_TILES 0
+#define GSA_PASS_DYNAMIC_TILES 1
 #endif
 
 // ---------------------------------------------------------------------------------
@@ -170,10 +170,10 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_radix_pass(const PassAr
 #endif
   for (int i = tid; i < WARPS * RADIX / 2; i += THREADS) reinterpret_cast<u32 *>(whist)[i] = 0;
   __syncthreads();
-  // Tiles are taken in blockIdx order: the look-back only ever waits on lower-numbered blocks, which
-  // the hardware dispatches first (as in CUB's decoupled look-back scan).  A ticket from a global
-  // counter (-DGSA_PASS_DYNAMIC_TILES=1) does not depend on that, but costs every tile an atomic
-  // round trip before it can start: 0.4-1.3 % of the pass.
+  // Tiles are taken by ticket from a global counter: the look-back then only ever waits on tiles whose CTAs are
+  // already resident and running, whatever order the hardware dispatches blocks in (with blockIdx as the tile id
+  // -- -DGSA_PASS_DYNAMIC_TILES=0, 0.4-1.3 % faster -- forward progress would rest on in-order dispatch, which CUDA
+  // does not promise, least of all with several builds sharing the device).
 #if GSA_PASS_DYNAMIC_TILES
   const u32 tile = s_tile;
 #else

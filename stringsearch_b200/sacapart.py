@@ -90,6 +90,23 @@ class PartitionedSuffixArray(StringIndex):
             pass
 
 
+class _DeviceBuffers:
+    """Grow-only device buffers reused between query batches (a fresh torch allocation per collective and call
+    means allocator traffic and cross-stream bookkeeping on every batch)."""
+
+    def __init__(self):
+        self._b = {}
+
+    def get(self, name: str, numel: int, dtype, dev):
+        import torch
+
+        t = self._b.get(name)
+        if t is None or t.numel() < numel or t.dtype != dtype or t.device != dev:
+            t = torch.empty(max(1, numel), dtype=dtype, device=dev)
+            self._b[name] = t
+        return t[:numel]
+
+
 def merge_results(starts: np.ndarray, lens: np.ndarray):
     """Host statement of the cross-rank merge rule used by the distributed query
     (sacapart lib.rs:86-92): starts/lens are [nsets, Q]; longer wins, equal length -> the
@@ -117,6 +134,7 @@ class DistributedPartitionedSuffixArray(StringIndex):
         self._device = device
         self._ps, self._np = partition_plan(self._text.size, num_partitions)
         self._halo = halo
+        self._bufs = _DeviceBuffers()
         self._shards = []  # (partition index, offset, handle)
         self.build_ms = []  # device time of every local shard build (gsa_build_stats.ms_total), in shard order
         for i in range(self.rank, self._np, self.world):
@@ -191,10 +209,11 @@ class DistributedPartitionedSuffixArray(StringIndex):
             hdr = torch.zeros(2, dtype=torch.int64, device=dev)
         if self.world > 1:
             dist.broadcast(hdr, src=src, group=self._group)
-        q, nbytes = int(hdr[0]), int(hdr[1])
+        h_host = hdr.tolist()
+        q, nbytes = int(h_host[0]), int(h_host[1])
         if self.rank != src:
-            t_off = torch.empty(q + 1, dtype=torch.int64, device=dev)
-            t_pat = torch.empty(max(1, nbytes), dtype=torch.uint8, device=dev)
+            t_off = self._bufs.get("off", q + 1, torch.int64, dev)
+            t_pat = self._bufs.get("pat", max(1, nbytes), torch.uint8, dev)
         if self.world > 1:
             dist.broadcast(t_off, src=src, group=self._group)
             dist.broadcast(t_pat, src=src, group=self._group)
@@ -202,16 +221,16 @@ class DistributedPartitionedSuffixArray(StringIndex):
         if max_len > self._halo + 1:
             raise ValueError(f"needle of {max_len} bytes exceeds the shard halo ({self._halo}); rebuild with a larger halo")
         # ---- local shards, ascending partition index --------------------------------------
-        t_start = torch.zeros(q, dtype=torch.int64, device=dev)
-        t_len = torch.zeros(q, dtype=torch.int32, device=dev)
+        t_start = self._bufs.get("start", q, torch.int64, dev).zero_()
+        t_len = self._bufs.get("len", q, torch.int32, dev).zero_()
         if self._shards:
             self._answer_local(t_pat, t_off, q, t_start, t_len, dev, max_len)
         else:
             t_start.fill_(2**62)  # a rank without shards never wins (len 0, huge start)
         # ---- gather + merge ---------------------------------------------------------------------
         if self.world > 1:
-            g_start = torch.empty(self.world * q, dtype=torch.int64, device=dev)
-            g_len = torch.empty(self.world * q, dtype=torch.int32, device=dev)
+            g_start = self._bufs.get("g_start", self.world * q, torch.int64, dev)
+            g_len = self._bufs.get("g_len", self.world * q, torch.int32, dev)
             dist.all_gather_into_tensor(g_start, t_start, group=self._group)
             dist.all_gather_into_tensor(g_len, t_len, group=self._group)
             if on_gpu:
@@ -259,6 +278,7 @@ class ReplicatedSuffixArray(StringIndex):
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self._text = N.as_u8(text)
         self._device = device
+        self._bufs = _DeviceBuffers()
         self._h = self._build()
 
     # device-touching steps (overridden with the oracle by the gloo CPU tests of the plumbing)
@@ -331,10 +351,11 @@ class ReplicatedSuffixArray(StringIndex):
             hdr = torch.zeros(2, dtype=torch.int64, device=dev)
         if self.world > 1:
             dist.broadcast(hdr, src=src, group=self._group)
-        q, nbytes = int(hdr[0]), int(hdr[1])
+        h_host = hdr.tolist()
+        q, nbytes = int(h_host[0]), int(h_host[1])
         if self.rank != src:
-            t_off = torch.empty(q + 1, dtype=torch.int64, device=dev)
-            t_pat = torch.empty(max(1, nbytes), dtype=torch.uint8, device=dev)
+            t_off = self._bufs.get("off", q + 1, torch.int64, dev)
+            t_pat = self._bufs.get("pat", max(1, nbytes), torch.uint8, dev)
         if self.world > 1:
             dist.broadcast(t_off, src=src, group=self._group)
             dist.broadcast(t_pat, src=src, group=self._group)
@@ -343,22 +364,22 @@ class ReplicatedSuffixArray(StringIndex):
         lo = min(q, self.rank * per)
         hi = min(q, lo + per)
         first = torch.int64 if what == "lsm" else torch.int32
-        t_start = torch.zeros(max(per, 1), dtype=first, device=dev)
-        t_len = torch.zeros(max(per, 1), dtype=torch.int32, device=dev)
+        t_start = self._bufs.get("a_" + what, max(per, 1), first, dev).zero_()
+        t_len = self._bufs.get("b_" + what, max(per, 1), torch.int32, dev).zero_()
         if hi > lo:
-            sub_off = t_off[lo:hi + 1].contiguous()
+            sub_off = t_off[lo:hi + 1]  # (a view: the kernels take any 8-byte aligned offset array)
             max_len = int((sub_off[1:] - sub_off[:-1]).max())
             if what == "lsm":
                 self._answer_local(t_pat, sub_off, hi - lo, t_start, t_len, dev, max_len)
             else:
                 self._answer_local_search_all(t_pat, sub_off, hi - lo, t_start, t_len, dev, max_len)
         if self.world > 1:
-            g_start = torch.empty(self.world * max(per, 1), dtype=first, device=dev)
-            g_len = torch.empty(self.world * max(per, 1), dtype=torch.int32, device=dev)
+            g_start = self._bufs.get("ga_" + what, self.world * max(per, 1), first, dev)
+            g_len = self._bufs.get("gb_" + what, self.world * max(per, 1), torch.int32, dev)
             dist.all_gather_into_tensor(g_start, t_start, group=self._group)
             dist.all_gather_into_tensor(g_len, t_len, group=self._group)
             t_start, t_len = g_start, g_len
-        return t_start[:q], t_len[:q]
+        return t_start[:q], t_len[:q]  # views of buffers that the next batch of the same kind overwrites
 
     def longest_substring_match(self, needle) -> LongestCommonSubstring:
         s, l = self.longest_substring_match_batch([needle])
