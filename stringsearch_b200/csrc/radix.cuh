@@ -55,6 +55,11 @@ __device__ __forceinline__ u64 key_of_suffix(const KeyGen &g, u32 i) {
   return x >> (64u - g.key_bits);
 }
 
+// Hint: move `bytes` (multiple of 16, 16-byte aligned address) from HBM into L2; no destination, nothing to wait for.
+__device__ __forceinline__ void l2_prefetch_bulk(const void *p, u32 bytes) {
+  if (bytes != 0u) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
 __device__ __forceinline__ void gen_key0(const KeyGen &g, u32 j, u64 &key, u32 &sufx) {
   const u32 i = (j < g.ns) ? (g.n - 1u - j) : (j - g.ns);
   key = key_of_suffix(g, i);
@@ -122,6 +127,7 @@ struct PassArgs {
   const u32 *bin_base; // [256] global exclusive offsets of this digit
   u32 *status;         // [tiles][256], zeroed before launch
   u32 *counter;        // dynamic tile id, zeroed before launch
+  u32 pf_dist;         // > 0: ask L2 to fetch the pairs of tile (mine + pf_dist) now (cp.async.bulk.prefetch.L2)
   KeyGen gen;          // GEN only
 };
 
@@ -132,6 +138,28 @@ struct PassCfg {
   // keys, values, per-warp digit counts (u16: a warp holds at most 32 * IPT elements, a tile offset is below TILE), bin offsets
   static constexpr size_t SMEM = (size_t)TILE * sizeof(KOUT) + (size_t)TILE * 4 + (size_t)WARPS * RADIX * 2 + RADIX * 4;
 };
+
+// The lowest lane of every set of equal digits claims `popc(peers)` slots of the warp's bin.  The leaders of one row
+// hold DISTINCT digits, hence distinct u16 counters: a plain load + store does what a shared-memory atomic would, and
+// a full-warp ATOMS costs ~2 cycles per active lane (64 per row on uniform digits: at 16 rows x 8 warps per tile
+// that pipe alone took as long as the tile's share of HBM time), a conflict-free LDS / STS pair a few.  Rows are ordered
+// by __syncwarp() (memory ordering among the lanes of the warp).  -DGSA_RANK_ATOMS=1 restores the atomic form.
+#ifndef GSA_RANK_ATOMS
+#define GSA_RANK_ATOMS 0
+#endif
+#if GSA_RANK_ATOMS
+#define GSA_CLAIM(base, wh, wh32, d, peers, below)                                                                   \
+  if ((below) == 0) (base) = (atomicAdd(&(wh32)[(d) >> 1], (u32)__popc(peers) << (16u * ((d) & 1u))) >> (16u * ((d) & 1u))) & 0xffffu
+#else
+#define GSA_CLAIM(base, wh, wh32, d, peers, below)          \
+  do {                                                      \
+    if ((below) == 0) {                                     \
+      (base) = (wh)[d];                                     \
+      (wh)[d] = (u16)((base) + (u32)__popc(peers));         \
+    }                                                       \
+    __syncwarp();                                           \
+  } while (0)
+#endif
 
 // Lanes of the warp whose 8-bit digit equals mine, from 8 ballots (cost independent of the
 // number of distinct digits in the warp).
@@ -181,6 +209,16 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_radix_pass(const PassAr
 #endif
   const u32 tile_base = tile * (u32)TILE;
   const u32 valid = min((u32)TILE, a.n - tile_base);
+  if (!GEN && a.pf_dist != 0u && tid == 0) {
+    // The tile that the CTA taking this SM slot after me will most likely get: its 48 KB move from HBM to L2 while
+    // the tiles in between are processed, so its loads meet L2 latency, not DRAM latency.
+    const u64 pb = (u64)tile_base + (u64)a.pf_dist * TILE;
+    if (pb < a.n) {
+      const u32 cnt = (u32)min((u64)TILE, (u64)a.n - pb);
+      l2_prefetch_bulk(static_cast<const KIN *>(a.keys_in) + pb, (cnt * (u32)sizeof(KIN)) & ~15u);
+      l2_prefetch_bulk(a.vals_in + pb, (cnt * 4u) & ~15u);
+    }
+  }
 
   // ---- load (warp-striped: element order inside the tile is (warp, k, lane)) ----------
   u64 key[IPT];
@@ -220,7 +258,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_radix_pass(const PassAr
     const u32 peers = peers_by_ballot(d);
     const u32 below = __popc(peers & lt);
     u32 base = 0;
-    if (below == 0) base = (atomicAdd(&wh32[d >> 1], (u32)__popc(peers) << (16u * (d & 1u))) >> (16u * (d & 1u))) & 0xffffu;
+    GSA_CLAIM(base, wh, wh32, d, peers, below);
     base = __shfl_sync(0xffffffffu, base, __ffs(peers) - 1);
     lrank[0] = base + below;
     use_match = __popc(__ballot_sync(0xffffffffu, below == 0)) <= 6;
@@ -232,7 +270,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_radix_pass(const PassAr
       const u32 peers = __match_any_sync(0xffffffffu, d);
       const u32 below = __popc(peers & lt);
       u32 base = 0;
-      if (below == 0) base = (atomicAdd(&wh32[d >> 1], (u32)__popc(peers) << (16u * (d & 1u))) >> (16u * (d & 1u))) & 0xffffu;
+      GSA_CLAIM(base, wh, wh32, d, peers, below);
       base = __shfl_sync(0xffffffffu, base, __ffs(peers) - 1);
       if (k & 1) lrank[k >> 1] |= (base + below) << 16; else lrank[k >> 1] = base + below;
     }
@@ -243,7 +281,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_radix_pass(const PassAr
       const u32 peers = peers_by_ballot(d);
       const u32 below = __popc(peers & lt);
       u32 base = 0;
-      if (below == 0) base = (atomicAdd(&wh32[d >> 1], (u32)__popc(peers) << (16u * (d & 1u))) >> (16u * (d & 1u))) & 0xffffu;
+      GSA_CLAIM(base, wh, wh32, d, peers, below);
       base = __shfl_sync(0xffffffffu, base, __ffs(peers) - 1);
       if (k & 1) lrank[k >> 1] |= (base + below) << 16; else lrank[k >> 1] = base + below;
     }
@@ -479,7 +517,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_radix_pass_p(const Pass
       const u32 peers = peers_by_ballot(d);
       const u32 below = __popc(peers & lt);
       u32 base = 0;
-      if (below == 0) base = (atomicAdd(&wh32[d >> 1], (u32)__popc(peers) << (16u * (d & 1u))) >> (16u * (d & 1u))) & 0xffffu;
+      GSA_CLAIM(base, wh, wh32, d, peers, below);
       base = __shfl_sync(0xffffffffu, base, __ffs(peers) - 1);
       lrank[0] = base + below;
       use_match = __popc(__ballot_sync(0xffffffffu, below == 0)) <= 6;
@@ -491,7 +529,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_radix_pass_p(const Pass
         const u32 peers = __match_any_sync(0xffffffffu, d);
         const u32 below = __popc(peers & lt);
         u32 base = 0;
-        if (below == 0) base = (atomicAdd(&wh32[d >> 1], (u32)__popc(peers) << (16u * (d & 1u))) >> (16u * (d & 1u))) & 0xffffu;
+        GSA_CLAIM(base, wh, wh32, d, peers, below);
         base = __shfl_sync(0xffffffffu, base, __ffs(peers) - 1);
         if (k & 1) lrank[k >> 1] |= (base + below) << 16; else lrank[k >> 1] = base + below;
       }
@@ -502,7 +540,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_radix_pass_p(const Pass
         const u32 peers = peers_by_ballot(d);
         const u32 below = __popc(peers & lt);
         u32 base = 0;
-        if (below == 0) base = (atomicAdd(&wh32[d >> 1], (u32)__popc(peers) << (16u * (d & 1u))) >> (16u * (d & 1u))) & 0xffffu;
+        GSA_CLAIM(base, wh, wh32, d, peers, below);
         base = __shfl_sync(0xffffffffu, base, __ffs(peers) - 1);
         if (k & 1) lrank[k >> 1] |= (base + below) << 16; else lrank[k >> 1] = base + below;
       }

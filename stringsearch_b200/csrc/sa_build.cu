@@ -1682,13 +1682,18 @@ static void launch_pass_p(const PassArgs &a, u32 L, cudaStream_t st) {
 // first pass then generates the keys and writes buffer 0).  *cur_out = buffer holding the
 // sorted pairs.  k_scan_hist (bin offsets + constant digits) has been launched by the caller.
 static int run_passes(const Layout &y, u32 L, int npass, int cur, const KeyGen *gen, cudaStream_t st,
-                      gsa_build_stats *stats, PassTimer &timer, int *cur_out, u32 *passes_done, u32 skip) {
+                      gsa_build_stats *stats, PassTimer &timer, int *cur_out, u32 *passes_done, u32 skip, int sms) {
   // `skip`: bit p = digit p is the same in every key (k_scan_hist), its pass would be the identity
   const u32 tiles = (u32)div_up(L, PASS_TILE);
   const size_t smem = PassCfg<PASS_THREADS, PASS_IPT>::SMEM;
   const char *cfg_env = getenv("GSA_PASS_CFG");  // experiments: alternative tile shapes of the pass kernel
   const int pass_cfg = cfg_env ? atoi(cfg_env) : 0;
   const u32 tiles_max = (u32)div_up(L, 2048);
+  // L2 prefetch distance of the pass kernel in tiles: one generation of resident CTAs ahead (a CTA asks L2 for the tile
+  // that its SM slot will most likely process next).  rep_1G: pass 0.576 -> 0.611 of the copy bandwidth, 268.8 -> 264.3 ms;
+  // half that distance does the same, twice that distance nothing (profiles/r2/README.md).  GSA_PASS_PF=0 switches it off.
+  const char *pf_env = getenv("GSA_PASS_PF");
+  const u32 pf_dist = pf_env ? (u32)atoi(pf_env) : (u32)(sms * PASS_MIN_BLOCKS);
   bool need_gen = gen != nullptr;
   u32 done = 0;
   for (int p = 0; p < npass; ++p) {
@@ -1700,6 +1705,7 @@ static int run_passes(const Layout &y, u32 L, int npass, int cur, const KeyGen *
     a.bin_base = y.bin_base + p * RADIX;
     a.counter = y.pass_status;
     a.status = y.pass_status + 256;
+    a.pf_dist = pf_dist;
     cudaEvent_t t0, t1;
     GSA_TRY_RC(timer.next(&t0));
     GSA_TRY_RC(timer.next(&t1));
@@ -1906,7 +1912,7 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
       GSA_TRY_RC(fetch_counters());
       skip0 = mailbox[10];
     }
-    GSA_TRY_RC(run_passes(y, n, npass0, 0, &gen, st, stats, timer, &cur, &passes, skip0));
+    GSA_TRY_RC(run_passes(y, n, npass0, 0, &gen, st, stats, timer, &cur, &passes, skip0, sms));
   }
   GSA_TRY(cudaEventRecord(ev[2], st));
 
@@ -2139,7 +2145,7 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
         cur = 0;
         if (stats) stats->kernel_launches++;
       } else {
-        GSA_TRY_RC(run_passes(y, S, npass, 0, nullptr, st, stats, timer, &cur, &passes, skip));
+        GSA_TRY_RC(run_passes(y, S, npass, 0, nullptr, st, stats, timer, &cur, &passes, skip, sms));
       }
       GSA_TRY(cudaEventRecord(ev[2], st));
       // SA slots of the sorted elements from the group tables
@@ -2241,7 +2247,7 @@ int stable_byte_order_device(const u8 *d_bytes, u32 n, u32 *d_order, u32 *d_coun
   a.keys_out = y.keys_out; a.vals_out = d_order;
   a.n = n; a.shift = 0;
   a.bin_base = y.bin_base;
-  a.counter = y.pass_status; a.status = y.pass_status + 256;
+  a.counter = y.pass_status; a.status = y.pass_status + 256; a.pf_dist = 0;
   a.gen = gen;
   k_radix_pass<PASS_THREADS, PASS_IPT, true><<<tiles, PASS_THREADS, smem, st>>>(a);
   KLAUNCH_CHECK();
