@@ -25,6 +25,9 @@ constexpr int MAX_PASSES = 8;
 #ifndef GSA_PASS_DYNAMIC_TILES
 #define GSA_PASS_DYNAMIC_TILES 1
 #endif
+#ifndef GSA_LB_WIDE
+#define GSA_LB_WIDE 0  // > 0: width of the far steps of the look-back (see k_radix_pass)
+#endif
 
 // ---------------------------------------------------------------------------------
 // Round-0 key generation from the bit-packed symbol stream.
@@ -165,12 +168,26 @@ struct PassCfg {
 // number of distinct digits in the warp).
 __device__ __forceinline__ u32 peers_by_ballot(u32 d) {
   u32 m = 0xffffffffu;
-#pragma unroll
-  for (int b = 0; b < RADIX_BITS; ++b) {
-    const u32 bit = (d >> b) & 1u;
-    const u32 bal = __ballot_sync(0xffffffffu, bit);
-    m &= bal ^ (bit - 1u);  // bit ? bal : ~bal
-  }
+  // Per bit: test -> predicate (LOP3.P), vote, predicate -> 0 / ~0 (SEL), m &= ~(ballot ^ that) (LOP3): 4 instructions.
+  // (Written in C -- `bal ^ (bit - 1)` or `p ? bal : ~bal` -- the compiler shifts, masks, compares and decrements: 6.)
+#define GSA_PEER_BIT(B)                                                  \
+  asm("{\n\t.reg .pred p;\n\t.reg .b32 t, bal;\n\t"                     \
+      "and.b32 t, %1, " #B ";\n\t"                                       \
+      "setp.ne.u32 p, t, 0;\n\t"                                         \
+      "vote.sync.ballot.b32 bal, p, 0xffffffff;\n\t"                     \
+      "selp.b32 t, 0xffffffff, 0, p;\n\t"                                \
+      "lop3.b32 %0, %0, bal, t, 0x90;\n\t}"                              \
+      : "+r"(m)                                                          \
+      : "r"(d))
+  GSA_PEER_BIT(1);
+  GSA_PEER_BIT(2);
+  GSA_PEER_BIT(4);
+  GSA_PEER_BIT(8);
+  GSA_PEER_BIT(16);
+  GSA_PEER_BIT(32);
+  GSA_PEER_BIT(64);
+  GSA_PEER_BIT(128);
+#undef GSA_PEER_BIT
   return m;
 }
 
@@ -224,6 +241,9 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_radix_pass(const PassAr
   u64 key[IPT];
   u32 val[IPT];
   const u32 wbase = tile_base + (u32)warp * (32u * IPT) + (u32)lane;
+  // (A variant without the per-element bounds checks for full tiles -- 6 instructions per element less in the load and
+  // in the scatter -- was SLOWER: 0.60 of the copy bandwidth with either, 0.57 with both, against 0.635: the compiler then
+  // issues the 32 loads / 32 stores of a thread back to back, and the bursts delay the other CTAs' memory operations.)
 #pragma unroll
   for (int k = 0; k < IPT; ++k) {
     const u32 idx = wbase + (u32)k * 32u;
@@ -353,6 +373,28 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_radix_pass(const PassAr
         }
         if (fin) break;
         t -= used;  // used == 0: the nearest predecessor is not ready yet, poll again
+#if GSA_LB_WIDE > 0
+        // All four were aggregates: the tiles just behind me have published, the nearest inclusive prefix is further back
+        // (about RT / tau tiles in steady state).  Walk there GSA_LB_WIDE tiles per round trip instead of four -- the wide
+        // window costs as many loads as the narrow trips it replaces, but they are independent.
+        while (used == 4 || used == GSA_LB_WIDE) {
+          u32 w[GSA_LB_WIDE];
+#pragma unroll
+          for (int j = 0; j < GSA_LB_WIDE; ++j) w[j] = (t - j >= 0) ? ld_volatile_u32(base + (size_t)(t - j) * RADIX) : done0;
+          used = 0;
+#pragma unroll
+          for (int j = 0; j < GSA_LB_WIDE; ++j) {
+            if (!fin && used == j && w[j] != 0u) {
+              excl += (w[j] & 0x7fffffffu) - 1u;
+              used = j + 1;
+              fin = (w[j] & 0x80000000u) != 0u;
+            }
+          }
+          t -= used;
+          if (fin) break;
+        }
+        if (fin) break;
+#endif
       }
       st_volatile_u32(a.status + (size_t)tile * RADIX + tid, st_pre(excl + pub));
     }
