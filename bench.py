@@ -880,6 +880,7 @@ def run_ours(args, rank, local_rank, world):
         "vs_baseline": None, "dtype": "u64 keys / u32 indices", "data": "synthetic",
         "config": config_of(args.workload, world),
         "clocks": r["clocks"],
+        "host_binding": cx.numa,
         "e2e": e2e,
         "gpu_launches": int(r["launches"]),
         "roofline": {

@@ -25,9 +25,6 @@ constexpr int MAX_PASSES = 8;
 #ifndef GSA_PASS_DYNAMIC_TILES
 #define GSA_PASS_DYNAMIC_TILES 1
 #endif
-#ifndef GSA_LB_WIDE
-#define GSA_LB_WIDE 0  // > 0: width of the far steps of the look-back (see k_radix_pass)
-#endif
 
 // ---------------------------------------------------------------------------------
 // Round-0 key generation from the bit-packed symbol stream.
@@ -357,6 +354,8 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_radix_pass(const PassAr
       const u32 *base = a.status + tid;
       i64 t = (i64)tile - 1;
       const u32 done0 = st_pre(0);  // virtual tiles in front of tile 0
+      // (Measured and dropped, profiles/r2/README.md: 8 / 16 tiles per far step, u16 aggregates with a 16 / 24 / 32 tile
+      // window, prefixes from a dedicated scanner CTA, one-lane polling of not-ready rows -- every one slower than this.)
       for (;;) {
         u32 s[4];
 #pragma unroll
@@ -373,28 +372,6 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_radix_pass(const PassAr
         }
         if (fin) break;
         t -= used;  // used == 0: the nearest predecessor is not ready yet, poll again
-#if GSA_LB_WIDE > 0
-        // All four were aggregates: the tiles just behind me have published, the nearest inclusive prefix is further back
-        // (about RT / tau tiles in steady state).  Walk there GSA_LB_WIDE tiles per round trip instead of four -- the wide
-        // window costs as many loads as the narrow trips it replaces, but they are independent.
-        while (used == 4 || used == GSA_LB_WIDE) {
-          u32 w[GSA_LB_WIDE];
-#pragma unroll
-          for (int j = 0; j < GSA_LB_WIDE; ++j) w[j] = (t - j >= 0) ? ld_volatile_u32(base + (size_t)(t - j) * RADIX) : done0;
-          used = 0;
-#pragma unroll
-          for (int j = 0; j < GSA_LB_WIDE; ++j) {
-            if (!fin && used == j && w[j] != 0u) {
-              excl += (w[j] & 0x7fffffffu) - 1u;
-              used = j + 1;
-              fin = (w[j] & 0x80000000u) != 0u;
-            }
-          }
-          t -= used;
-          if (fin) break;
-        }
-        if (fin) break;
-#endif
       }
       st_volatile_u32(a.status + (size_t)tile * RADIX + tid, st_pre(excl + pub));
     }
