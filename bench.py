@@ -597,7 +597,7 @@ def bench_queries(cx: Ctx, n=QUERY_N, Q=QUERY_Q, m=QUERY_M, steps=3):
     rsa = sacapart.ReplicatedSuffixArray(t, cx.local_rank)  # every rank builds its own copy (deterministic)
     h = rsa._h
     res = {"text": f"{n >> 20} MiB ACGT (seed 5)", "patterns": Q, "pattern_len": m, "gpus": cx.world,
-           "api": "sacapart.ReplicatedSuffixArray.query_device: pattern broadcast, rank r answers its 1/N of the needles "
+           "api": "sacapart.ReplicatedSuffixArray.query_device: rank 0 sends every rank its 1/N of the needles (header broadcast + grouped NCCL send/recv), rank r answers them "
                   "(gsa_lsm_device / gsa_search_all_device), one all-gather per result array"}
     flat = off = t_pat = t_off = None
     if cx.rank == 0:
@@ -618,7 +618,7 @@ def bench_queries(cx: Ctx, n=QUERY_N, Q=QUERY_Q, m=QUERY_M, steps=3):
         ms = cx.max_over_ranks(e0.elapsed_time(e1) / steps)
         out[what] = (a, b)
         res[key] = {"queries_per_s": Q / (ms / 1e3), "ms": ms,
-                    "includes": ("pattern broadcast + all-gather of the two result arrays over NCCL" if cx.world > 1 else
+                    "includes": ("header broadcast, point-to-point scatter of the needle slices, all-gather of the two result arrays over NCCL" if cx.world > 1 else
                                  "ReplicatedSuffixArray.query_device at world 1: header / max-length reductions and result allocation around the kernel")}
         if cx.world == 1:
             # the kernel alone: patterns, offsets and result arrays resident, one launch per step

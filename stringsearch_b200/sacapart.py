@@ -265,9 +265,12 @@ class ReplicatedSuffixArray(StringIndex):
     "1 GiB SA, 8 GPUs" -- pure data parallelism over the needles, answers identical to one GPU).
 
     Every rank builds its own copy (the construction is deterministic, so the copies are equal
-    and no suffix array travels between GPUs); a query batch is broadcast from `src`, rank r
-    answers needles [r * ceil(Q / W), (r + 1) * ceil(Q / W)), and one all-gather per result
-    array puts the answers together on every rank."""
+    and no suffix array travels between GPUs); rank r answers needles [r * ceil(Q / W),
+    (r + 1) * ceil(Q / W)) of a batch held by `src`, which sends every rank its slice, and one
+    all-gather per result array puts the answers together on every rank."""
+
+    CHUNKS = 4              # pieces a rank's slice of a batch travels in (transfer of piece k + 1 overlaps the search of piece k)
+    CHUNK_MIN = 1 << 16     # ... when a piece holds at least this many needles
 
     def __init__(self, text, device: int, group=None):
         import torch.distributed as dist
@@ -337,49 +340,113 @@ class ReplicatedSuffixArray(StringIndex):
 
     def query_device(self, t_pat, t_off, what: str = "lsm", src: int = 0):
         """One query batch on device tensors (collective).  On rank `src`: `t_pat` uint8 pattern
-        bytes and `t_off` int64 offsets [Q + 1] on this rank's GPU; ignored elsewhere.  The batch is
-        broadcast, rank r answers needles [r * ceil(Q / W), (r + 1) * ceil(Q / W)) against its copy
-        of the index, and one all-gather per result array puts the answers together.
+        bytes and `t_off` int64 offsets [Q + 1] on this rank's GPU; ignored elsewhere.  Rank r answers
+        needles [r * ceil(Q / W), (r + 1) * ceil(Q / W)) against its copy of the index, so it is sent
+        exactly those: a small header (batch size, longest needle, the byte range of every rank's slice)
+        is broadcast, then `src` sends every rank its offsets and pattern bytes point to point (one
+        grouped NCCL launch; over NVSwitch the W - 1 transfers run side by side, and 1 / W of the batch
+        travels to each GPU instead of all of it), and one all-gather per result array puts the answers
+        together on every rank.
         what = "lsm" -> (start int64 [Q], len int32 [Q]); "search_all" -> (left int32, count int32)."""
         import torch
 
         dist = self._dist
+        W = self.world
         dev = torch.device("cuda", self._device) if torch.cuda.is_available() else torch.device("cpu")
-        if self.rank == src:
-            hdr = torch.tensor([t_off.numel() - 1, t_pat.numel()], dtype=torch.int64, device=dev)
-        else:
-            hdr = torch.zeros(2, dtype=torch.int64, device=dev)
-        if self.world > 1:
-            dist.broadcast(hdr, src=src, group=self._group)
-        h_host = hdr.tolist()
-        q, nbytes = int(h_host[0]), int(h_host[1])
-        if self.rank != src:
-            t_off = self._bufs.get("off", q + 1, torch.int64, dev)
-            t_pat = self._bufs.get("pat", max(1, nbytes), torch.uint8, dev)
-        if self.world > 1:
-            dist.broadcast(t_off, src=src, group=self._group)
-            dist.broadcast(t_pat, src=src, group=self._group)
-        # my slice of the batch: the offsets stay absolute, so the pattern buffer is shared as is
-        per = (q + self.world - 1) // self.world if q else 0
-        lo = min(q, self.rank * per)
-        hi = min(q, lo + per)
         first = torch.int64 if what == "lsm" else torch.int32
-        t_start = self._bufs.get("a_" + what, max(per, 1), first, dev).zero_()
-        t_len = self._bufs.get("b_" + what, max(per, 1), torch.int32, dev).zero_()
-        if hi > lo:
-            sub_off = t_off[lo:hi + 1]  # (a view: the kernels take any 8-byte aligned offset array)
-            max_len = int((sub_off[1:] - sub_off[:-1]).max())
-            if what == "lsm":
-                self._answer_local(t_pat, sub_off, hi - lo, t_start, t_len, dev, max_len)
+        if W == 1:
+            q = t_off.numel() - 1
+            t_a = self._bufs.get("a_" + what, max(q, 1), first, dev).zero_()
+            t_b = self._bufs.get("b_" + what, max(q, 1), torch.int32, dev).zero_()
+            if q > 0:
+                self._answer(what, t_pat, t_off, q, t_a, t_b, dev, int((t_off[1:] - t_off[:-1]).max()))
+            return t_a[:q], t_b[:q]
+        # ---- header: q, longest needle, byte offset of the first needle of every (rank, chunk) piece (+ the end) ----
+        CH = self.CHUNKS
+
+        def plan(q):
+            """needle index where piece (r, k) starts, for r in ranks, k in chunks, + q at the end"""
+            per = (q + W - 1) // W if q else 0
+            ch = CH if per >= self.CHUNK_MIN * CH else 1
+            cs = (per + ch - 1) // ch if per else 0
+            starts = []
+            for r in range(W):
+                r_lo, r_hi = min(q, r * per), min(q, (r + 1) * per)
+                starts += [min(r_hi, r_lo + k * cs) if k < ch else r_hi for k in range(CH)]
+            return per, starts + [q]
+
+        if self.rank == src:
+            q = t_off.numel() - 1
+            _, starts = plan(q)
+            cuts = torch.tensor(starts, dtype=torch.int64, device=dev)
+            longest = (t_off[1:] - t_off[:-1]).max().view(1) if q else torch.zeros(1, dtype=torch.int64, device=dev)
+            hdr = torch.cat([torch.tensor([q], dtype=torch.int64, device=dev), longest, t_off[cuts]])
+        else:
+            hdr = torch.zeros(W * CH + 3, dtype=torch.int64, device=dev)
+        dist.broadcast(hdr, src=src, group=self._group)
+        h_host = hdr.tolist()  # the one host round trip of a batch: buffer sizes depend on it
+        q, max_len, cut_bytes = int(h_host[0]), int(h_host[1]), [int(x) for x in h_host[2:]]
+        per, starts = plan(q)
+        mine = range(self.rank * CH, (self.rank + 1) * CH)
+        lo, hi = starts[mine[0]], starts[mine[-1] + 1]
+        blo, bhi = cut_bytes[mine[0]], cut_bytes[mine[-1] + 1]
+        # ---- every rank gets its slice of the offsets and of the pattern bytes, chunk after chunk: one grouped NCCL
+        # launch per chunk, all issued now; the search of chunk k starts when chunk k has arrived, while the later
+        # chunks are still on the wire ---------------------------------------------------------------------------
+        if self.rank == src:
+            my_off = t_off[lo:hi + 1]
+            my_pat = t_pat[blo:bhi] if bhi > blo else t_pat[:1]
+        else:
+            my_off = self._bufs.get("off", max(1, hi - lo), torch.int64, dev)
+            my_pat = self._bufs.get("pat", max(1, bhi - blo), torch.uint8, dev)
+            peer_src = dist.get_global_rank(self._group, src) if self._group is not None else src
+        arrivals = []
+        for k in range(CH):
+            ops = []
+            if self.rank == src:
+                for r in range(W):
+                    p0, p1 = starts[r * CH + k], starts[r * CH + k + 1]
+                    if r == src or p1 == p0:
+                        continue
+                    peer = dist.get_global_rank(self._group, r) if self._group is not None else r
+                    # piece (r, k): the start offsets of its needles (the end offset of a piece is in the header)
+                    ops.append(dist.P2POp(dist.isend, t_off[p0:p1], peer, self._group))
+                    c0, c1 = cut_bytes[r * CH + k], cut_bytes[r * CH + k + 1]
+                    if c1 > c0:
+                        ops.append(dist.P2POp(dist.isend, t_pat[c0:c1], peer, self._group))
             else:
-                self._answer_local_search_all(t_pat, sub_off, hi - lo, t_start, t_len, dev, max_len)
-        if self.world > 1:
-            g_start = self._bufs.get("ga_" + what, self.world * max(per, 1), first, dev)
-            g_len = self._bufs.get("gb_" + what, self.world * max(per, 1), torch.int32, dev)
-            dist.all_gather_into_tensor(g_start, t_start, group=self._group)
-            dist.all_gather_into_tensor(g_len, t_len, group=self._group)
-            t_start, t_len = g_start, g_len
-        return t_start[:q], t_len[:q]  # views of buffers that the next batch of the same kind overwrites
+                p0, p1 = starts[mine[0] + k], starts[mine[0] + k + 1]
+                if p1 > p0:
+                    ops.append(dist.P2POp(dist.irecv, my_off[p0 - lo:p1 - lo], peer_src, self._group))
+                    c0, c1 = cut_bytes[mine[0] + k], cut_bytes[mine[0] + k + 1]
+                    if c1 > c0:
+                        ops.append(dist.P2POp(dist.irecv, my_pat[c0 - blo:c1 - blo], peer_src, self._group))
+            arrivals.append(dist.batch_isend_irecv(ops) if ops else [])
+        t_a = self._bufs.get("a_" + what, max(per, 1), first, dev).zero_()
+        t_b = self._bufs.get("b_" + what, max(per, 1), torch.int32, dev).zero_()
+        rel = self._bufs.get("rel", hi - lo + 1, torch.int64, dev)
+        for k in range(CH):
+            for req in arrivals[k]:
+                req.wait()
+            p0, p1 = starts[mine[0] + k], starts[mine[0] + k + 1]
+            if p1 == p0:
+                continue
+            # offsets into my slice of the pattern bytes; the end offset of the piece comes from the header
+            piece = rel[p0 - lo:p1 - lo + 1]
+            torch.sub(my_off[p0 - lo:p1 - lo], blo, out=piece[:-1])
+            piece[-1:].fill_(cut_bytes[mine[0] + k + 1] - blo)
+            self._answer(what, my_pat, piece, p1 - p0, t_a[p0 - lo:p1 - lo], t_b[p0 - lo:p1 - lo], dev, max_len)
+        g_a = self._bufs.get("ga_" + what, W * max(per, 1), first, dev)
+        g_b = self._bufs.get("gb_" + what, W * max(per, 1), torch.int32, dev)
+        dist.all_gather_into_tensor(g_a, t_a, group=self._group)
+        dist.all_gather_into_tensor(g_b, t_b, group=self._group)
+        return g_a[:q], g_b[:q]  # views of buffers that the next batch of the same kind overwrites
+
+    def _answer(self, what, t_pat, t_off, q, t_a, t_b, dev, max_len):
+        if what == "lsm":
+            self._answer_local(t_pat, t_off, q, t_a, t_b, dev, max_len)
+        else:
+            self._answer_local_search_all(t_pat, t_off, q, t_a, t_b, dev, max_len)
 
     def longest_substring_match(self, needle) -> LongestCommonSubstring:
         s, l = self.longest_substring_match_batch([needle])

@@ -41,6 +41,12 @@ def replicated(text, rank, world, local):
     if rank == 0:
         eleft, ecnt = port.search_all_batch(text, sa, needles)
         ok = ok and bool((left == eleft).all() and (cnt == ecnt).all())
+    # the same batch with every rank's slice travelling (and answered) in pieces, as large batches do
+    rsa.CHUNK_MIN = 100
+    s2, l2 = rsa.longest_substring_match_batch(needles)
+    left2, cnt2 = rsa.search_all_batch(needles)
+    if rank == 0:
+        ok = ok and bool((s2 == es).all() and (l2 == el).all() and (left2 == eleft).all() and (cnt2 == ecnt).all())
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, src=0)
     dist.barrier()

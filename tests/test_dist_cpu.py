@@ -74,7 +74,7 @@ def test_distributed_query_plumbing_gloo(P, port):
         assert ok, (rank, got, expect)
 
 
-def _worker_replicated(rank, world, port_no, text_bytes, needles, expect, q):
+def _worker_replicated(rank, world, port_no, text_bytes, needles, expect, q, chunk_min=1 << 16):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import torch.distributed as dist
@@ -89,6 +89,8 @@ def _worker_replicated(rank, world, port_no, text_bytes, needles, expect, q):
     answered = []
 
     class OracleReplica(ReplicatedSuffixArray):
+        CHUNK_MIN = chunk_min  # 1: every rank's slice travels (and is answered) in up to CHUNKS pieces
+
         def _build(self):
             return port.sa_build(self._text)
 
@@ -111,21 +113,23 @@ def _worker_replicated(rank, world, port_no, text_bytes, needles, expect, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("nq", [0, 1, 2, 5, 6])
-def test_replicated_query_plumbing_gloo(nq, port):
+@pytest.mark.parametrize("nq,chunk_min,world", [(0, 1 << 16, 2), (1, 1 << 16, 2), (2, 1, 2), (5, 1 << 16, 2), (6, 1 << 16, 2), (6, 1, 2),
+                                                (19, 1, 2), (23, 1, 3), (7, 1 << 16, 3)])
+def test_replicated_query_plumbing_gloo(nq, chunk_min, world, port):
     """ReplicatedSuffixArray: the batch is split across the ranks (each answers only its slice) and
     the gathered answers are those of one un-partitioned index, in order."""
     text = ("This is a rather long text. We can probably find matches that span two partitions. Oh yes. " * 2).encode()
-    needles = [b"rather long", b"text. We can", b"zzz", b"Oh yes. This", b"", b"We can probably"][:nq]
+    needles = ([b"rather long", b"text. We can", b"zzz", b"Oh yes. This", b"", b"We can probably"] * 4)[:nq]
+    port_base = 0
     sa = port.sa_build(text)
     expect = [tuple(port.longest_substring_match(text, sa, nd)) for nd in needles]
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port_no = 31500 + (os.getpid() % 2000) + nq
-    procs = [ctx.Process(target=_worker_replicated, args=(r, 2, port_no, text, needles, expect, q)) for r in range(2)]
+    port_no = 31500 + (os.getpid() % 2000) + nq + (30 if chunk_min == 1 else 0) + 60 * (world - 2)
+    procs = [ctx.Process(target=_worker_replicated, args=(r, world, port_no, text, needles, expect, q, chunk_min)) for r in range(world)]
     for p in procs:
         p.start()
-    res = [q.get(timeout=120) for _ in range(2)]
+    res = [q.get(timeout=120) for _ in range(world)]
     for p in procs:
         p.join(timeout=60)
     for rank, ok, got in res:
