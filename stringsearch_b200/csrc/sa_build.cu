@@ -1017,6 +1017,8 @@ struct RebuildArgs {
   u32 *tile_head;      // [tiles] k_tail_summary: last head slot + 1 inside the tile (or 0)
   const u32 *next_tail;  // [tiles] k_tail_scan: first tail slot in any later tile
   const u32 *prev_head;  // [tiles] k_tail_scan: last head slot + 1 in any earlier tile
+  u32 *surv_list;      // RB_SPARSE: the suffixes that are not unique yet are listed here (any order) ...
+  u32 *surv_count;     // ... so that round 1 walks them instead of all n text positions
 };
 
 // Loads the IPT consecutive elements of this thread plus one neighbour on each side and
@@ -1272,12 +1274,28 @@ __global__ void __launch_bounds__(THREADS, 2) k_rebuild(const RebuildArgs a) {
     if (lane == 31 && inc) wb = atomicAdd(a.bag_desc_count, inc);
     dbase = __shfl_sync(0xffffffffu, wb, 31) + inc - nd;
   }
+  // sparse round 0: the few survivors are listed (one reservation per warp), round 1 then walks that list
+  u32 sbase = 0;
+  if (MODE == RB_SPARSE) {
+    const u32 vm = (nvalid >= 32u) ? 0xffffffffu : ((1u << nvalid) - 1u);
+    const u32 ns = (u32)__popc(~(f & (f >> 1)) & vm);  // not (head and tail) = not unique yet
+    u32 inc = ns;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const u32 y = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += y;
+    }
+    u32 wb = 0;
+    if (lane == 31 && inc) wb = atomicAdd(a.surv_count, inc);
+    sbase = __shfl_sync(0xffffffffu, wb, 31) + inc - ns;
+  }
   u32 head = eh;  // head slot + 1
 #pragma unroll
   for (int j = 0; j < IPT; ++j) {
     if ((u32)j < nvalid) {
       if ((f >> j) & 1u) head = px[j] + 1u;
       const u32 s1 = head, e1 = tl[j] + 1u;  // label range of the group: [s1, e1]
+      if (MODE == RB_SPARSE && s1 != e1) a.surv_list[sbase++] = sx[j + 1];
       if (s1 == e1) {
         a.SA[px[j]] = (i32)sx[j + 1];
         if (MODE == RB_NORMAL) a.rank[sx[j + 1]] = RANK_DEAD | s1;
@@ -1840,7 +1858,7 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
   u32 k = k_want;
   if (const char *k_env = getenv("GSA_KEY_SYMBOLS")) {  // experiments: force the round-0 depth
     k = (u32)atoi(k_env);
-  } else if (k_want < k_max && n >= (1u << 22)) {
+  } else if (k_want < k_max && n >= (1u << 23)) {  // (below 8 MiB the probe's host round trip costs more than a wrong depth)
     // ... unless the text is repetitive: then nearly everything survives round 0 whatever its
     // depth, and a deeper start means fewer doubling rounds.
     constexpr u32 M = 1u << 16, TBL = 1u << 18;
@@ -1908,7 +1926,7 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
     u32 skip0 = 0;
     k_scan_hist<<<npass0, RADIX, 0, st>>>(y.ghist, y.bin_base, n, y.skip_mask);
     KLAUNCH_CHECK();
-    if (n >= SYNC_WORTH) {  // a constant digit (a^n ...) saves a pass over all n suffixes
+    if (n >= 8 * SYNC_WORTH) {  // a constant digit (a^n ...) saves a pass over all n suffixes: worth a round trip from 8 Mi on
       GSA_TRY_RC(fetch_counters());
       skip0 = mailbox[10];
     }
@@ -1951,6 +1969,7 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
     r.tiny_max = sparse ? 0u : tiny_conf;
     r.bag_desc = y.keys[kv ^ 1];  // the other half of the sort's double buffer is free until the next walk
     r.bag_desc_count = y.bag_count + 2;
+    r.surv_list = y.lst[0]; r.surv_count = y.ctr + 18;  // (round 0, sparse mode only; the word is zero from the start)
     if (round0) k_tail_summary<RB_THREADS, RB_IPT, true><<<tiles, RB_THREADS, 0, st>>>(r);
     else k_tail_summary<RB_THREADS, RB_IPT, false><<<tiles, RB_THREADS, 0, st>>>(r);
     KLAUNCH_CHECK();
@@ -2017,10 +2036,14 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
   log_round(k, n, n, 0, key_bits, passes, 0);
 
   // ---- doubling rounds ------------------------------------------------------------------------
-  int lcur = 0;        // lst buffer holding the candidates (text order); round 1 uses 0..n-1
+  int lcur = 0;        // lst buffer holding the candidates (text order); round 1 uses 0..n-1 ...
   u32 Lcand = n;       // candidates to walk
   u32 live = survivors;
   bool ident = true;
+  if (sparse && !getenv("GSA_NO_SURV_LIST")) {  // ... unless round 0 listed its few survivors (k_rebuild<RB_SPARSE>, any order)
+    Lcand = survivors;
+    ident = false;
+  }
   u64 h = k;           // suffixes are sorted by their first h symbols
   const u32 kb = 2 * lab_bits;
   const int npass = (int)div_up(kb, 8);
