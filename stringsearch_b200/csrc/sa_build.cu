@@ -30,6 +30,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <atomic>
 #include <vector>
 
 #include "radix.cuh"
@@ -1777,13 +1778,35 @@ static int run_passes(const Layout &y, u32 L, int npass, int cur, const KeyGen *
   return GSA_OK;
 }
 
+// 64 counter words + 256 alphabet words of page-locked host memory per calling thread (allocated once, portable across
+// devices, released when the thread ends).
+static u32 *host_mailbox() {
+  struct Box {
+    u32 *p = nullptr;
+    ~Box() { if (p) cudaFreeHost(p); }
+  };
+  static thread_local Box box;
+  if (box.p == nullptr && cudaHostAlloc(reinterpret_cast<void **>(&box.p), (64 + 256) * sizeof(u32), cudaHostAllocPortable) != cudaSuccess) {
+    cudaGetLastError();
+    box.p = nullptr;
+  }
+  return box.p;
+}
+
 int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t workspace_bytes, cudaStream_t st,
                     gsa_build_stats *stats) {
   if (stats) memset(stats, 0, sizeof(*stats));
   if (n == 0) return GSA_OK;
   static_assert(PASS_THREADS >= RADIX, "");
+  int sms = kDefaultSMs;
   {
-    // opt in to > 48 KB dynamic shared memory (idempotent, per device)
+    // opt in to > 48 KB dynamic shared memory: once per device and process (seven driver calls otherwise paid by every build)
+    static std::atomic<unsigned long long> configured{0};
+    int dev = 0;
+    GSA_TRY(cudaGetDevice(&dev));
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const unsigned long long bit = (dev >= 0 && dev < 64) ? (1ull << dev) : 0ull;
+    if (bit == 0ull || !(configured.load(std::memory_order_acquire) & bit)) {
     const int smem = (int)PassCfg<PASS_THREADS, PASS_IPT>::SMEM;
     GSA_TRY(cudaFuncSetAttribute(k_prefilter<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PF_SMEM));
     GSA_TRY(cudaFuncSetAttribute(k_prefilter<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PF_SMEM));
@@ -1792,6 +1815,8 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
     GSA_TRY(cudaFuncSetAttribute(k_radix_pass<256, 12, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PassCfg<256, 12>::SMEM));
     GSA_TRY(cudaFuncSetAttribute(k_radix_pass<384, 16, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PassCfg<384, 16>::SMEM));
     GSA_TRY(cudaFuncSetAttribute(k_radix_pass<512, 12, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PassCfg<512, 12>::SMEM));
+    configured.fetch_or(bit, std::memory_order_release);
+    }
   }
   char *owned = nullptr;
   const size_t need = build_workspace_bytes(n);
@@ -1811,12 +1836,6 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
   const size_t mis = (256 - (reinterpret_cast<uintptr_t>(workspace) & 255)) & 255;
   const Layout y = make_layout(static_cast<char *>(workspace) + mis, n);
 
-  int sms = kDefaultSMs;
-  {
-    int dev = 0;
-    GSA_TRY(cudaGetDevice(&dev));
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  }
   cudaEvent_t ev[4];
   for (auto &e : ev) GSA_TRY(cudaEventCreate(&e));
   struct EvFree { cudaEvent_t *e; ~EvFree() { for (int i = 0; i < 4; ++i) cudaEventDestroy(e[i]); } } ev_guard{ev};
@@ -1834,8 +1853,12 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
     k_byte_presence<<<blocks, 256, 0, st>>>(d_T, n, y.present);
     KLAUNCH_CHECK();
   }
-  u32 present[256];
-  GSA_TRY(cudaMemcpyAsync(present, y.present, sizeof(present), cudaMemcpyDeviceToHost, st));
+  // Everything the host reads back lands in a small page-locked block owned by the calling thread: a copy into pageable
+  // memory (a stack array) goes through the driver's staging path, ~10 us more per round trip, and a 4 MiB text pays six.
+  u32 *const hostbox = host_mailbox();
+  if (hostbox == nullptr) { set_error("cudaHostAlloc of the 2 KiB read-back block failed", __FILE__, __LINE__); return GSA_ENOMEM; }
+  u32 *const present = hostbox + 64;
+  GSA_TRY(cudaMemcpyAsync(present, y.present, 256 * sizeof(u32), cudaMemcpyDeviceToHost, st));
   GSA_TRY(cudaStreamSynchronize(st));
   CodeMap cm;
   u32 sigma = 0;
@@ -1868,9 +1891,9 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
     KeyGen probe{y.packed, n, 0, b, k_want * b};
     k_sample_dups<<<M / 256, 256, 0, st>>>(probe, M, table, TBL - 1, y.survivors);
     KLAUNCH_CHECK();
-    u32 dups = 0;
-    GSA_TRY(cudaMemcpyAsync(&dups, y.survivors, sizeof(u32), cudaMemcpyDeviceToHost, st));
+    GSA_TRY(cudaMemcpyAsync(hostbox, y.survivors, sizeof(u32), cudaMemcpyDeviceToHost, st));
     GSA_TRY(cudaStreamSynchronize(st));
+    const u32 dups = hostbox[0];
     if (dups > M / 8) k = k_max;
     // ... and if the sampled suffixes fall into very few classes the text consists of a few huge
     // groups: those are cheap to refine (their inert majority is not sorted), so a 32-bit start
@@ -1913,9 +1936,9 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
   // kernel.  Sync points per doubling round: after the gather (how much is live / to be sorted, which digits
   // are constant) and at the end (survivors, bag, huge groups); large rounds add one before the rebuild (is
   // this the last round?), small ones do not bother.
-  u32 mailbox[64];
+  u32 *const mailbox = hostbox;
   auto fetch_counters = [&]() -> int {
-    GSA_TRY(cudaMemcpyAsync(mailbox, y.ctr, sizeof(mailbox), cudaMemcpyDeviceToHost, st));
+    GSA_TRY(cudaMemcpyAsync(mailbox, y.ctr, 64 * sizeof(u32), cudaMemcpyDeviceToHost, st));
     GSA_TRY(cudaStreamSynchronize(st));
     return GSA_OK;
   };
