@@ -1037,6 +1037,7 @@ struct RebuildArgs {
   u32 *tile_head;      // [tiles] k_tail_summary: last head slot + 1 inside the tile (or 0)
   const u32 *next_tail;  // [tiles] k_tail_scan: first tail slot in any later tile
   const u32 *prev_head;  // [tiles] k_tail_scan: last head slot + 1 in any earlier tile
+  bool sa_holds_sufx;  // round 0: sufx IS the SA (slot l already holds suffix sufx[l]): no SA writes at all
   u32 *surv_list;      // RB_SPARSE: the suffixes that are not unique yet are listed here (any order) ...
   u32 *surv_count;     // ... so that round 1 walks them instead of all n text positions
 };
@@ -1316,8 +1317,9 @@ __global__ void __launch_bounds__(THREADS, 2) k_rebuild(const RebuildArgs a) {
       if ((f >> j) & 1u) head = px[j] + 1u;
       const u32 s1 = head, e1 = tl[j] + 1u;  // label range of the group: [s1, e1]
       if (MODE == RB_SPARSE && s1 != e1) a.surv_list[sbase++] = sx[j + 1];
+      const bool write_sa = !(ROUND0 && a.sa_holds_sufx);
       if (s1 == e1) {
-        a.SA[px[j]] = (i32)sx[j + 1];
+        if (write_sa) a.SA[px[j]] = (i32)sx[j + 1];
         if (MODE == RB_NORMAL) a.rank[sx[j + 1]] = RANK_DEAD | s1;
       } else {
         const u32 old = ROUND0 ? 0u : (u32)(kx[j + 1] >> a.lab_bits);
@@ -1331,7 +1333,7 @@ __global__ void __launch_bounds__(THREADS, 2) k_rebuild(const RebuildArgs a) {
         const u32 lab = keep ? old : pick_label(s1 - 1u, e1 - 1u, inert_owner ? old : 0u, a.tiny_max);
         const bool by_table = ROUND0 && is_huge_label(lab);  // members are labelled by k_rank_huge0
         if (lab != old && !by_table) a.rank[sx[j + 1]] = lab;
-        if (tiny) a.SA[px[j]] = (i32)sx[j + 1];  // provisional order: the bag is backed by SA
+        if (tiny && write_sa) a.SA[px[j]] = (i32)sx[j + 1];  // provisional order: the bag is backed by SA
         if ((f >> j) & 1u) {  // group head: publish the group's slot range
           if (tiny) {
             a.bag_desc[dbase++] = (u64)(s1 - 1u) | ((u64)size << 32);
@@ -1344,7 +1346,7 @@ __global__ void __launch_bounds__(THREADS, 2) k_rebuild(const RebuildArgs a) {
             }
           }
         }
-        if (MODE == RB_SPARSE) a.SA[px[j]] = (i32)sx[j + 1];
+        if (MODE == RB_SPARSE && write_sa) a.SA[px[j]] = (i32)sx[j + 1];
       }
     }
   }
@@ -1719,8 +1721,11 @@ static void launch_pass_p(const PassArgs &a, u32 L, cudaStream_t st) {
 // in y.ghist.  `cur` is the buffer index holding the input (ignored when gen != null: the
 // first pass then generates the keys and writes buffer 0).  *cur_out = buffer holding the
 // sorted pairs.  k_scan_hist (bin offsets + constant digits) has been launched by the caller.
+// `final_vals` (round 0): the LAST pass writes its values (the suffixes in sorted order) there instead of the ping-pong buffer --
+// the caller passes the SA itself, which round 0 would otherwise fill with a copy of exactly that sequence.
 static int run_passes(const Layout &y, u32 L, int npass, int cur, const KeyGen *gen, cudaStream_t st,
-                      gsa_build_stats *stats, PassTimer &timer, int *cur_out, u32 *passes_done, u32 skip, int sms) {
+                      gsa_build_stats *stats, PassTimer &timer, int *cur_out, u32 *passes_done, u32 skip, int sms,
+                      u32 *final_vals = nullptr, const u32 **vals_sorted = nullptr) {
   // `skip`: bit p = digit p is the same in every key (k_scan_hist), its pass would be the identity
   const u32 tiles = (u32)div_up(L, PASS_TILE);
   const size_t smem = PassCfg<PASS_THREADS, PASS_IPT>::SMEM;
@@ -1734,8 +1739,19 @@ static int run_passes(const Layout &y, u32 L, int npass, int cur, const KeyGen *
   const u32 pf_dist = pf_env ? (u32)atoi(pf_env) : (u32)(sms * PASS_MIN_BLOCKS);
   bool need_gen = gen != nullptr;
   u32 done = 0;
+  int last_p = -1;  // the last pass that will run
+  {
+    bool ng = need_gen;
+    for (int p = 0; p < npass; ++p) {
+      if (((skip >> p) & 1u) && !(ng && p == npass - 1)) continue;
+      last_p = p;
+      ng = false;
+    }
+  }
+  const u32 *vals_now = gen ? nullptr : y.vals[cur];
   for (int p = 0; p < npass; ++p) {
     if (((skip >> p) & 1u) && !(need_gen && p == npass - 1)) continue;  // constant digit: identity pass
+    u32 *const vdst_alt = (final_vals != nullptr && p == last_p) ? final_vals : nullptr;
     GSA_TRY(cudaMemsetAsync(y.pass_status, 0, (256 + (size_t)(pass_cfg ? tiles_max : tiles) * RADIX) * sizeof(u32), st));
     PassArgs a;
     a.n = L;
@@ -1750,7 +1766,7 @@ static int run_passes(const Layout &y, u32 L, int npass, int cur, const KeyGen *
     GSA_TRY(cudaEventRecord(t0, st));
     if (need_gen) {
       a.keys_in = nullptr; a.vals_in = nullptr;
-      a.keys_out = y.keys[0]; a.vals_out = y.vals[0];
+      a.keys_out = y.keys[0]; a.vals_out = vdst_alt ? vdst_alt : y.vals[0];
       a.gen = *gen;
       if (pass_cfg == 10) launch_pass_p<512, 8, true, 2>(a, L, st);
       else if (pass_cfg == 11) launch_pass_p<256, 16, true, 2>(a, L, st);
@@ -1759,7 +1775,7 @@ static int run_passes(const Layout &y, u32 L, int npass, int cur, const KeyGen *
       need_gen = false;
     } else {
       a.keys_in = y.keys[cur]; a.vals_in = y.vals[cur];
-      a.keys_out = y.keys[cur ^ 1]; a.vals_out = y.vals[cur ^ 1];
+      a.keys_out = y.keys[cur ^ 1]; a.vals_out = vdst_alt ? vdst_alt : y.vals[cur ^ 1];
       a.gen = KeyGen{};
       if (pass_cfg == 1) {
         k_radix_pass<256, 12, false, 4><<<(u32)div_up(L, 256 * 12), 256, PassCfg<256, 12>::SMEM, st>>>(a);
@@ -1781,6 +1797,7 @@ static int run_passes(const Layout &y, u32 L, int npass, int cur, const KeyGen *
       cur ^= 1;
     }
     KLAUNCH_CHECK();
+    vals_now = a.vals_out;
     GSA_TRY(cudaEventRecord(t1, st));
     ++done;
     if (stats) {
@@ -1793,6 +1810,7 @@ static int run_passes(const Layout &y, u32 L, int npass, int cur, const KeyGen *
   }
   if (stats) stats->kernel_launches++;  // k_scan_hist
   *cur_out = cur;
+  if (vals_sorted) *vals_sorted = vals_now;
   *passes_done = done;
   return GSA_OK;
 }
@@ -1949,6 +1967,7 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
   }
   int cur = 0;
   u32 passes = 0;
+  const u32 *sufx0 = nullptr;  // round 0: where the sorted suffixes are (the SA itself unless GSA_NO_SA_ALIAS)
   PassTimer timer;
   // Host <-> device traffic of the control flow: every counter the host needs lives in one 64-word block
   // (y.ctr), read back with ONE copy per sync point (`mailbox`); the counters of a round are zeroed by one
@@ -1972,7 +1991,8 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
       GSA_TRY_RC(fetch_counters());
       skip0 = mailbox[10];
     }
-    GSA_TRY_RC(run_passes(y, n, npass0, 0, &gen, st, stats, timer, &cur, &passes, skip0, sms));
+    GSA_TRY_RC(run_passes(y, n, npass0, 0, &gen, st, stats, timer, &cur, &passes, skip0, sms,
+                          getenv("GSA_NO_SA_ALIAS") ? nullptr : reinterpret_cast<u32 *>(d_SA), &sufx0));
   }
   GSA_TRY(cudaEventRecord(ev[2], st));
 
@@ -1997,7 +2017,8 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
     const u32 tiles = (u32)div_up(L, RB_TILE);
     GSA_TRY(cudaMemsetAsync(y.survivors, 0, sizeof(u32), st));  // (also the probe's / the sparse mode's scratch counter)
     RebuildArgs r;
-    r.keys = y.keys[kv]; r.sufx = y.vals[kv];
+    r.keys = y.keys[kv]; r.sufx = (round0 && sufx0 != nullptr) ? sufx0 : y.vals[kv];
+    r.sa_holds_sufx = round0 && r.sufx == reinterpret_cast<const u32 *>(d_SA);
     r.pos_in = round0 ? nullptr : y.slots;
     r.L = L;
     r.short_from = round0 ? (n - ns) : 0xffffffffu;
