@@ -1136,51 +1136,62 @@ __global__ void __launch_bounds__(THREADS) k_tail_summary(const RebuildArgs a) {
 // With these two per-tile carries the rebuild kernels need no look-back between their blocks.
 __global__ void __launch_bounds__(1024) k_tail_scan(const u32 *__restrict__ tile_tail, u32 *__restrict__ next_tail, u32 tiles,
                                                     const u32 *__restrict__ tile_head, u32 *__restrict__ prev_head) {
-  __shared__ u32 s_v[1024];
-  const u32 t = threadIdx.x;
-  const u32 per = (tiles + 1023u) / 1024u;
-  const u32 lo = min(tiles, t * per), hi = min(tiles, lo + per);
-  if (tile_head != nullptr) {  // exclusive prefix-max over the chunk maxima, then inside the chunk
-    u32 m = 0;
-    for (u32 i = lo; i < hi; ++i) m = max(m, tile_head[i]);
-    s_v[t] = m;
-    __syncthreads();
-    u32 x = (t > 0) ? s_v[t - 1] : 0u;
-    __syncthreads();
-    s_v[t] = x;
-    __syncthreads();
-    for (u32 o = 1; o < 1024; o <<= 1) {
-      const u32 y = (t >= o) ? s_v[t - o] : 0u;
-      __syncthreads();
-      s_v[t] = max(s_v[t], y);
-      __syncthreads();
-    }
-    u32 carry = s_v[t];
-    for (u32 i = lo; i < hi; ++i) {
-      prev_head[i] = carry;
-      carry = max(carry, tile_head[i]);
-    }
-    __syncthreads();
+  // One block; warp w owns a contiguous span of the tiles and walks it in rows of 32 (coalesced loads, a shuffle scan per
+  // row, a running carry), after a first walk that gives every warp the carry it starts from.  (One thread per chunk with
+  // sequential dependent loads took 76-120 us per launch at 1 GiB -- 25 launches per build.)
+  __shared__ u32 s_max[32], s_min[32];
+  const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const u32 span = (((tiles + 31u) / 32u) + 31u) / 32u * 32u;  // tiles per warp, a multiple of 32
+  const u32 lo = min(tiles, warp * span), hi = min(tiles, lo + span);
+  u32 m = 0, mn = NO_TAIL;
+  for (u32 i = lo + lane; i < hi; i += 32u) {
+    if (tile_head != nullptr) m = max(m, tile_head[i]);
+    mn = min(mn, tile_tail[i]);
   }
-  u32 m = NO_TAIL;
-  for (u32 i = lo; i < hi; ++i) m = min(m, tile_tail[i]);
-  s_v[t] = m;
-  __syncthreads();
-  // exclusive suffix-min over the 1024 chunk minima (Hillis-Steele on a copy shifted by one)
-  u32 x = (t + 1 < 1024) ? s_v[t + 1] : NO_TAIL;
-  __syncthreads();
-  s_v[t] = x;
-  __syncthreads();
-  for (u32 o = 1; o < 1024; o <<= 1) {
-    const u32 y = (t + o < 1024) ? s_v[t + o] : NO_TAIL;
-    __syncthreads();
-    s_v[t] = min(s_v[t], y);
-    __syncthreads();
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
   }
-  u32 carry = s_v[t];  // min over all chunks to the right of mine
-  for (u32 i = hi; i > lo; --i) {
-    next_tail[i - 1] = carry;
-    carry = min(carry, tile_tail[i - 1]);
+  if (lane == 0) { s_max[warp] = m; s_min[warp] = mn; }
+  __syncthreads();
+  u32 cmax = 0, cmin = NO_TAIL;  // max over the warps in front of mine, min over the warps behind it
+  for (u32 w = 0; w < 32u; ++w) {
+    if (w < warp) cmax = max(cmax, s_max[w]);
+    if (w > warp) cmin = min(cmin, s_min[w]);
+  }
+  if (tile_head != nullptr) {  // prev_head[t] = max over tiles t' < t of tile_head[t']
+    u32 carry = cmax;
+    for (u32 base = lo; base < hi; base += 32u) {
+      const u32 i = base + lane;
+      u32 inc = (i < hi) ? tile_head[i] : 0u;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const u32 y = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= (u32)o) inc = max(inc, y);
+      }
+      u32 exc = __shfl_up_sync(0xffffffffu, inc, 1);
+      if (lane == 0) exc = 0u;
+      if (i < hi) prev_head[i] = max(carry, exc);
+      carry = max(carry, __shfl_sync(0xffffffffu, inc, 31));
+    }
+  }
+  {  // next_tail[t] = min over tiles t' > t of tile_tail[t'] (slots ascend, so the minimum is the nearest)
+    u32 carry = cmin;
+    const u32 rows = (hi - lo + 31u) / 32u;
+    for (u32 r = rows; r > 0; --r) {
+      const u32 i = lo + (r - 1u) * 32u + lane;
+      u32 inc = (i < hi) ? tile_tail[i] : NO_TAIL;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const u32 y = __shfl_down_sync(0xffffffffu, inc, o);
+        if (lane + (u32)o < 32u) inc = min(inc, y);
+      }
+      u32 exc = __shfl_down_sync(0xffffffffu, inc, 1);
+      if (lane == 31) exc = NO_TAIL;
+      if (i < hi) next_tail[i] = min(carry, exc);
+      carry = min(carry, __shfl_sync(0xffffffffu, inc, 0));
+    }
   }
 }
 
