@@ -260,6 +260,21 @@ class DistributedPartitionedSuffixArray(StringIndex):
             pass
 
 
+def slice_plan(q: int, world: int, chunks: int, chunk_min: int):
+    """How a batch of `q` needles is cut for `world` ranks: rank r answers needles [r * per, (r + 1) * per) with
+    per = ceil(q / world), and its slice travels in up to `chunks` pieces (one piece when a piece would hold fewer than
+    `chunk_min` needles).  Returns (per, starts): starts[r * chunks + k] = first needle of piece k of rank r,
+    starts[world * chunks] = q; empty pieces repeat the end of their rank's slice."""
+    per = (q + world - 1) // world if q else 0
+    ch = chunks if per >= chunk_min * chunks else 1
+    cs = (per + ch - 1) // ch if per else 0
+    starts = []
+    for r in range(world):
+        r_lo, r_hi = min(q, r * per), min(q, (r + 1) * per)
+        starts += [min(r_hi, r_lo + k * cs) if k < ch else r_hi for k in range(chunks)]
+    return per, starts + [q]
+
+
 class ReplicatedSuffixArray(StringIndex):
     """The un-partitioned index on every GPU, queries split across the ranks (SURVEY.md 8(e):
     "1 GiB SA, 8 GPUs" -- pure data parallelism over the needles, answers identical to one GPU).
@@ -365,15 +380,7 @@ class ReplicatedSuffixArray(StringIndex):
         CH = self.CHUNKS
 
         def plan(q):
-            """needle index where piece (r, k) starts, for r in ranks, k in chunks, + q at the end"""
-            per = (q + W - 1) // W if q else 0
-            ch = CH if per >= self.CHUNK_MIN * CH else 1
-            cs = (per + ch - 1) // ch if per else 0
-            starts = []
-            for r in range(W):
-                r_lo, r_hi = min(q, r * per), min(q, (r + 1) * per)
-                starts += [min(r_hi, r_lo + k * cs) if k < ch else r_hi for k in range(CH)]
-            return per, starts + [q]
+            return slice_plan(q, W, CH, self.CHUNK_MIN)
 
         if self.rank == src:
             q = t_off.numel() - 1

@@ -279,3 +279,25 @@ def test_accel_model_matches_oracle(port):
                 assert ac.search_all(p) == (left, cnt), (sigma, n, bits, p, ac.search_all(p), (left, cnt))
                 cases += 1
     assert cases > 3000
+
+
+def test_slice_plan_covers_every_needle_once():
+    """ReplicatedSuffixArray's cut of a batch: pieces are contiguous, ordered, cover [0, q) exactly, a rank's pieces stay
+    inside its slice [r * per, (r + 1) * per), and small slices travel in one piece."""
+    from stringsearch_b200.sacapart import slice_plan
+
+    for world in (1, 2, 3, 4, 8):
+        for chunks in (1, 4):
+            for chunk_min in (1, 5, 1 << 16):
+                for q in list(range(0, 70)) + [1000, 4097, 10_000_000]:
+                    per, starts = slice_plan(q, world, chunks, chunk_min)
+                    assert len(starts) == world * chunks + 1 and starts[0] == 0 and starts[-1] == q
+                    assert all(a <= b for a, b in zip(starts, starts[1:]))
+                    assert per * world >= q and (per == 0) == (q == 0)
+                    for r in range(world):
+                        lo, hi = min(q, r * per), min(q, (r + 1) * per)
+                        mine = starts[r * chunks:(r + 1) * chunks + 1]
+                        assert mine[0] == lo and mine[-1] == hi
+                        pieces = [b - a for a, b in zip(mine, mine[1:]) if b > a]
+                        if per < chunk_min * chunks:
+                            assert len(pieces) <= 1
