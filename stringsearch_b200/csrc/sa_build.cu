@@ -1040,7 +1040,13 @@ struct RebuildArgs {
   bool sa_holds_sufx;  // round 0: sufx IS the SA (slot l already holds suffix sufx[l]): no SA writes at all
   u32 *surv_list;      // RB_SPARSE: the suffixes that are not unique yet are listed here (any order) ...
   u32 *surv_count;     // ... so that round 1 walks them instead of all n text positions
+  // round 0: k_tail_summary also lists the INDICES of the elements that are not unique (while they are rare); when round 0
+  // turns out sparse and all groups are small, k_rebuild_list handles just those instead of a pass over all n elements
+  u32 *live_idx;       // [<= L / 4] indices into the sorted sequence, any order
+  u32 *live_idx_ctl;   // [0] entries, [1] != 0: some warp saw too many to list, [2] != 0: k_rebuild_list met a large group
 };
+constexpr u32 LIVE_IDX_PER_WARP = 64;  // a warp (32 * IPT elements) lists at most this many; more = not a sparse text
+constexpr u32 LIST_GROUP_MAX = 64;     // k_rebuild_list walks groups up to this size, larger ones go the general way
 
 // Loads the IPT consecutive elements of this thread plus one neighbour on each side and
 // returns the flag bits f (bit j = flag of element l0 + j, j = 0..IPT; beyond-the-end counts
@@ -1112,11 +1118,36 @@ __global__ void __launch_bounds__(THREADS) k_tail_summary(const RebuildArgs a) {
     }
     surv = (u32)__popc(~(f & (f >> 1)) & vm);  // not (head and tail) = not unique yet
   }
+  const u32 my_surv = surv;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
     hd = max(hd, __shfl_xor_sync(0xffffffffu, hd, o));
     surv += __shfl_xor_sync(0xffffffffu, surv, o);
+  }
+  if (ROUND0 && a.live_idx != nullptr && surv != 0u) {  // (warp-uniform) list the warp's non-unique elements while they are few
+    if (surv > LIVE_IDX_PER_WARP) {
+      if (lane == 0) a.live_idx_ctl[1] = 1u;
+    } else {
+      u32 inc = my_surv;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const u32 y = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += y;
+      }
+      u32 base = 0;
+      if (lane == 31) base = atomicAdd(a.live_idx_ctl, inc);
+      base = __shfl_sync(0xffffffffu, base, 31) + inc - my_surv;
+      if (my_surv) {
+        const u32 nvalid = min((u32)IPT, a.L - l0);
+        u32 m = ~(f & (f >> 1)) & ((1u << nvalid) - 1u);
+        while (m) {
+          const u32 j = (u32)__ffs(m) - 1u;
+          m &= m - 1u;
+          a.live_idx[base++] = l0 + j;
+        }
+      }
+    }
   }
   __shared__ u32 s_s[WARPS], s_h[WARPS];
   if (lane == 0) { s_w[warp] = v; s_s[warp] = surv; s_h[warp] = hd; }
@@ -1193,6 +1224,36 @@ __global__ void __launch_bounds__(1024) k_tail_scan(const u32 *__restrict__ tile
       carry = min(carry, __shfl_sync(0xffffffffu, inc, 0));
     }
   }
+}
+
+// Round 0 of a sparse text (few elements are not unique, all of them in small groups): the rebuild proper for just the
+// listed elements -- what k_rebuild<ROUND0, RB_SPARSE> does for them, without its pass over all n elements (which reads
+// 12 bytes per element to find that nearly every one is unique: 1.2 of rand_256M's 11.9 ms).  One thread per listed
+// element walks to the two ends of its group (flags as in load_and_flag); a group of more than LIST_GROUP_MAX elements
+// raises ctl[2] and the host runs the general kernel instead (every write here is one the general kernel repeats).
+__global__ void __launch_bounds__(256) k_rebuild_list(const RebuildArgs a, const u32 count) {
+  const u32 q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= count) return;
+  const u32 l = a.live_idx[q];
+  const u32 L = a.L;
+  auto flagged = [&](u32 x) -> bool {  // element x starts a group (x == L: beyond the end)
+    if (x == 0u || x >= L) return true;
+    return a.keys[x] != a.keys[x - 1u] || a.sufx[x] >= a.short_from || a.sufx[x - 1u] >= a.short_from;
+  };
+  u32 h = l, t = l;
+  u32 steps = 0;
+  while (!flagged(h)) { --h; if (++steps > LIST_GROUP_MAX) break; }
+  while (steps <= LIST_GROUP_MAX && !flagged(t + 1u)) { ++t; if (++steps > LIST_GROUP_MAX) break; }
+  if (steps > LIST_GROUP_MAX || t - h + 1u >= HUGE_T) {
+    a.live_idx_ctl[2] = 1u;
+    return;
+  }
+  // group = slots [h, t] (round 0: slot == index), t > h because the element is not unique
+  const u32 lab = pick_label(h, t, 0u, 0u);
+  const u32 sfx = a.sufx[l];
+  a.rank[sfx] = lab;
+  a.surv_list[atomicAdd(a.surv_count, 1u)] = sfx;
+  if (l == h) a.G[lab] = (u64)h | ((u64)t << 32);
 }
 
 // MODE (the survivor count of the round is known from k_tail_summary before the launch):
@@ -2024,6 +2085,9 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
   u32 tiny_conf = getenv("GSA_NO_BAG") ? 0u : TINY_MAX;
   if (const char *e = getenv("GSA_TINY_MAX")) tiny_conf = std::min<u32>(TINY_MAX, (u32)atoi(e));
   int bcur = 0;  // bag buffer the rebuild of the current round appends to (= input of the next round)
+  bool list_used = false;  // round 0 went through k_rebuild_list
+  RebuildArgs r0_args{};
+  u32 r0_tiles = 0;
   auto launch_rebuild = [&](bool round0, u32 rnd, u32 L, int kv, bool may_finish) -> int {
     const u32 tiles = (u32)div_up(L, RB_TILE);
     GSA_TRY(cudaMemsetAsync(y.survivors, 0, sizeof(u32), st));  // (also the probe's / the sparse mode's scratch counter)
@@ -2044,6 +2108,9 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
     r.bag_desc = y.keys[kv ^ 1];  // the other half of the sort's double buffer is free until the next walk
     r.bag_desc_count = y.bag_count + 2;
     r.surv_list = y.lst[0]; r.surv_count = y.ctr + 18;  // (round 0, sparse mode only; the word is zero from the start)
+    const bool list_live = round0 && !getenv("GSA_NO_LIVE_LIST");
+    r.live_idx = list_live ? y.slots : nullptr;       // (free in round 0)
+    r.live_idx_ctl = y.ctr + 19;                      // words 19, 20, 21: zero from the start
     if (round0) k_tail_summary<RB_THREADS, RB_IPT, true><<<tiles, RB_THREADS, 0, st>>>(r);
     else k_tail_summary<RB_THREADS, RB_IPT, false><<<tiles, RB_THREADS, 0, st>>>(r);
     KLAUNCH_CHECK();
@@ -2064,9 +2131,22 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
       }
     }
     if (round0) {
-      if (fin) k_rebuild<RB_THREADS, RB_IPT, true, RB_FINAL><<<tiles, RB_THREADS, 0, st>>>(r);
-      else if (sparse) k_rebuild<RB_THREADS, RB_IPT, true, RB_SPARSE><<<tiles, RB_THREADS, 0, st>>>(r);
-      else k_rebuild<RB_THREADS, RB_IPT, true, RB_NORMAL><<<tiles, RB_THREADS, 0, st>>>(r);
+      // sparse, every non-unique element listed by k_tail_summary: handle just those (the caller checks ctl[2] at its next
+      // read-back and falls back to the general kernel if a large group was met)
+      list_used = sparse && !fin && r.sa_holds_sufx && r.live_idx != nullptr && mailbox[20] == 0u && mailbox[19] == surv_bound;
+      r0_args = r;
+      r0_tiles = tiles;
+      if (fin && r.sa_holds_sufx) {
+        // everything is unique and the SA already holds the order: nothing left to write
+      } else if (fin) {
+        k_rebuild<RB_THREADS, RB_IPT, true, RB_FINAL><<<tiles, RB_THREADS, 0, st>>>(r);
+      } else if (list_used) {
+        k_rebuild_list<<<(u32)div_up(surv_bound, 256), 256, 0, st>>>(r, surv_bound);
+      } else if (sparse) {
+        k_rebuild<RB_THREADS, RB_IPT, true, RB_SPARSE><<<tiles, RB_THREADS, 0, st>>>(r);
+      } else {
+        k_rebuild<RB_THREADS, RB_IPT, true, RB_NORMAL><<<tiles, RB_THREADS, 0, st>>>(r);
+      }
     } else {
       if (fin) k_rebuild<RB_THREADS, RB_IPT, false, RB_FINAL><<<tiles, RB_THREADS, 0, st>>>(r);
       else k_rebuild<RB_THREADS, RB_IPT, false, RB_NORMAL><<<tiles, RB_THREADS, 0, st>>>(r);
@@ -2085,6 +2165,12 @@ int build_sa_device(const u8 *d_T, i32 *d_SA, u32 n, void *workspace, size_t wor
   GSA_TRY(cudaMemsetAsync(y.hkt_labels, 0, (size_t)y.hkt_cap * sizeof(u32), st));
   GSA_TRY_RC(launch_rebuild(true, 0, n, cur, true));
   GSA_TRY_RC(fetch_counters());  // end of round 0: survivors, bag entries, huge groups
+  if (list_used && mailbox[21] != 0u) {  // a group too large for k_rebuild_list: the general kernel redoes round 0's rebuild
+    GSA_TRY(cudaMemsetAsync(y.ctr + 18, 0, sizeof(u32), st));
+    k_rebuild<RB_THREADS, RB_IPT, true, RB_SPARSE><<<r0_tiles, RB_THREADS, 0, st>>>(r0_args);
+    KLAUNCH_CHECK();
+    GSA_TRY_RC(fetch_counters());
+  }
   u32 survivors = mailbox[14];
   u32 nbag = mailbox[bcur];     // entries of bag buffer bcur
   u32 hc = mailbox[4 + hcur];   // huge groups entering round 1

@@ -115,6 +115,35 @@ def test_sparse_mode_on_and_off(port, monkeypatch):
     monkeypatch.delenv("GSA_KEY_SYMBOLS", raising=False)
 
 
+def test_sparse_round0_list_rebuild(port, monkeypatch):
+    """Sparse round 0: the few non-unique elements are listed by k_tail_summary and handled by k_rebuild_list alone.
+    Texts with short runs (groups above the list kernel's size limit, some of them straddling warps and tiles: fallback to
+    the general kernel), with one dense spot (a warp sees too many to list), and plain random text; same SA with the
+    list switched off."""
+    from stringsearch_b200 import synth
+
+    rng = np.random.default_rng(21)
+    texts = [synth.random_bytes(700_000, 31), synth.acgt(1_200_000, 32)]
+    t = synth.random_bytes(900_000, 33).copy()
+    for ln in (40, 66, 70, 75, 90, 130, 66, 69):  # runs of one byte: groups of about ln - key depth suffixes
+        o = int(rng.integers(0, t.size - 200))
+        t[o:o + ln] = 65
+    texts.append(t)
+    t = synth.random_bytes(1_000_000, 34).copy()
+    t[500_000:503_000] = 66  # one dense spot: ~3000 non-unique suffixes side by side (still sparse: 1e6 / 64 = 15625)
+    texts.append(t)
+    t = synth.acgt(800_000, 35).copy()
+    t[1000:1100] = t[400_000:400_100]  # a repeat: ~100 groups of two
+    texts.append(t)
+    for i, t in enumerate(texts):
+        exp = port.sa_build(t)
+        monkeypatch.delenv("GSA_NO_LIVE_LIST", raising=False)
+        _assert_same(_sort(t), exp, f"text {i}, list rebuild allowed")
+        monkeypatch.setenv("GSA_NO_LIVE_LIST", "1")
+        _assert_same(_sort(t), exp, f"text {i}, list rebuild off")
+    monkeypatch.delenv("GSA_NO_LIVE_LIST", raising=False)
+
+
 def test_fuzz_repetitive_structures(ref):
     """Randomised periodic / run-heavy / copy-heavy texts with groups from a few hundred to a few hundred thousand suffixes
     (the group tables start at 512): every combination of verdicts (label moved, group became small, unique,
