@@ -1125,9 +1125,10 @@ __global__ void __launch_bounds__(THREADS) k_tail_summary(const RebuildArgs a) {
     hd = max(hd, __shfl_xor_sync(0xffffffffu, hd, o));
     surv += __shfl_xor_sync(0xffffffffu, surv, o);
   }
+  bool too_many = false;  // (warp-uniform) this warp saw more non-unique elements than it lists
   if (ROUND0 && a.live_idx != nullptr && surv != 0u) {  // (warp-uniform) list the warp's non-unique elements while they are few
     if (surv > LIVE_IDX_PER_WARP) {
-      if (lane == 0) a.live_idx_ctl[1] = 1u;
+      too_many = true;
     } else {
       u32 inc = my_surv;
 #pragma unroll
@@ -1149,16 +1150,19 @@ __global__ void __launch_bounds__(THREADS) k_tail_summary(const RebuildArgs a) {
       }
     }
   }
-  __shared__ u32 s_s[WARPS], s_h[WARPS];
-  if (lane == 0) { s_w[warp] = v; s_s[warp] = surv; s_h[warp] = hd; }
+  __shared__ u32 s_s[WARPS], s_h[WARPS], s_o[WARPS];
+  if (lane == 0) { s_w[warp] = v; s_s[warp] = surv; s_h[warp] = hd; s_o[warp] = too_many ? 1u : 0u; }
   __syncthreads();
   if (tid == 0) {
-    u32 m = NO_TAIL, t = 0, h = 0;
+    u32 m = NO_TAIL, t = 0, h = 0, o = 0;
 #pragma unroll
-    for (int w = 0; w < WARPS; ++w) { m = min(m, s_w[w]); t += s_s[w]; h = max(h, s_h[w]); }
+    for (int w = 0; w < WARPS; ++w) { m = min(m, s_w[w]); t += s_s[w]; h = max(h, s_h[w]); o |= s_o[w]; }
     a.tile_tail[tile] = m;
     a.tile_head[tile] = h;
     if (t) atomicAdd(a.survivors, t);
+    // one look per block, a store only while the word is still zero: every warp of a repetitive text ends up here, and four
+    // million stores to one address cost round 0 of rep_1G 4 ms
+    if (ROUND0 && o && __ldcg(a.live_idx_ctl + 1) == 0u) a.live_idx_ctl[1] = 1u;
   }
 }
 
