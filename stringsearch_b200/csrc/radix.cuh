@@ -260,7 +260,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_radix_pass(const PassAr
 
   // ---- per-warp digit counts and warp-local stable ranks in one step -----------------------
   // For each row k the lanes holding the same digit elect their lowest lane, which claims
-  // `count` slots of the warp's bin with one shared-memory atomic (with return) and hands the
+  // `count` slots of the warp's bin (GSA_CLAIM: a plain u16 load + store, the leaders' digits are distinct) and hands the
   // base to its peers; local rank = base + number of peers in lower lanes.  Rows are issued in
   // order by the converged warp, so equal digits keep their (k, lane) order: stable.
   // Peer masks come from match.any when the first row shows few distinct digits in the warp
@@ -268,7 +268,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_radix_pass(const PassAr
   u32 lrank[IPT / 2];  // two u16 per register
   const u32 lt = lanemask_lt();
   u16 *wh = whist + warp * RADIX;
-  u32 *wh32 = reinterpret_cast<u32 *>(wh);  // shared-memory atomics work on the 32-bit word holding the bin's half
+  [[maybe_unused]] u32 *wh32 = reinterpret_cast<u32 *>(wh);  // (GSA_RANK_ATOMS form: the atomic works on the 32-bit word holding the bin's half)
   bool use_match;
   {
     const u32 d = (u32)(key[0] >> a.shift) & 255u;
@@ -462,7 +462,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_radix_pass_p(const Pass
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const u32 lt = lanemask_lt();
   u16 *wh = whist + warp * RADIX;
-  u32 *wh32 = reinterpret_cast<u32 *>(wh);
+  [[maybe_unused]] u32 *wh32 = reinterpret_cast<u32 *>(wh);
 
   // thread 0: the loader.  issue(t, b): bulk copies of tile t into buffer b, completion on mbar[b]
   auto issue = [&](u32 t, int b) {
